@@ -1,0 +1,85 @@
+"""TEST INFRASTRUCTURE ONLY -- loads the UNMODIFIED reference Python files by path.
+
+Works only where `/root/reference` is mounted (the build container).  Nothing in the `-m gpu`
+tests, `smoke()` or `bench.py` imports this module; it exists to generate `tests/golden/` and to
+validate `oracle/d3m_oracle.c` against the real reference on CPU.
+
+Shims:
+  * `back_project.py` hard-codes `.cuda()` (:25,26,41) -> on this GPU-less box `torch.Tensor.cuda`
+    is replaced by the identity for the duration of a call;
+  * `tsdf_volume.py` imports `skimage` and `pycuda` (:6, :23-25), neither installed -> stub modules;
+    `TSDFVolume(use_gpu=False)` then runs the numba/numpy CPU path, whose colour branch raises
+    IndexError at :293 *after* tsdf/weight were updated (:285-286) -> caught by `integrate_cpu`.
+"""
+import contextlib
+import importlib.util
+import os
+import sys
+import types
+
+REF_ROOT = "/root/reference"
+_BP = os.path.join(REF_ROOT, "deep3dmap/core/voxel/back_project.py")
+_TSDF = os.path.join(REF_ROOT, "deep3dmap/core/tsdf/tsdf_volume.py")
+
+
+def available():
+    return os.path.exists(_BP) and os.path.exists(_TSDF)
+
+
+def _load(path, name):
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+_bp_mod = None
+_tsdf_mod = None
+
+
+def back_project_module():
+    global _bp_mod
+    if _bp_mod is None:
+        _bp_mod = _load(_BP, "_ref_back_project")
+    return _bp_mod
+
+
+def tsdf_module():
+    global _tsdf_mod
+    if _tsdf_mod is None:
+        for name in ("skimage", "skimage.measure", "pycuda", "pycuda.driver", "pycuda.autoinit", "pycuda.compiler"):
+            if name not in sys.modules:
+                sys.modules[name] = types.ModuleType(name)
+        sys.modules["skimage"].measure = sys.modules["skimage.measure"]
+        sys.modules["pycuda"].driver = sys.modules["pycuda.driver"]
+        sys.modules["pycuda.compiler"].SourceModule = object
+        _tsdf_mod = _load(_TSDF, "_ref_tsdf_volume")
+    return _tsdf_mod
+
+
+@contextlib.contextmanager
+def cpu_cuda_shim():
+    import torch
+    if torch.cuda.is_available():
+        yield
+        return
+    orig = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        yield
+    finally:
+        torch.Tensor.cuda = orig
+
+
+def back_project(coords, origin, voxel_size, feats, KRcam):
+    """Run the reference function on torch tensors (CPU here)."""
+    with cpu_cuda_shim():
+        return back_project_module().back_project(coords, origin, voxel_size, feats, KRcam)
+
+
+def integrate_cpu(vol, depth_im, cam_intr, cam_pose, obs_weight=1.0):
+    """`TSDFVolume.integrate(None, ...)` on the CPU path, swallowing the reference's colour crash."""
+    try:
+        vol.integrate(None, depth_im, cam_intr, cam_pose, obs_weight)
+    except IndexError:
+        pass
