@@ -1,0 +1,85 @@
+"""ctypes binding of `libd3m.so` (C ABI declared in `include/d3m.h`).
+
+There is deliberately NO fallback: if the CUDA library has not been built, or no CUDA device is
+present, every compute entry point raises.  Build with `python -m deep3dmap_b200.build`.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libd3m.so")
+
+# every symbol include/d3m.h declares
+SYMBOLS = (
+    "d3m_version", "d3m_last_error", "d3m_device_count",
+    "d3m_feats_nchw_to_nhwc", "d3m_feats_nhwc_to_nchw",
+    "d3m_back_project_fwd_workspace", "d3m_back_project_fwd",
+    "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
+    "d3m_tsdf_create", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_integrate_host",
+    "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches",
+)
+
+COORDS_F32, COORDS_I64, COORDS_I32 = 0, 1, 2
+TSDF_KERNEL_SEMANTICS, TSDF_TORCH_SEMANTICS, TSDF_WITH_COLOR = 0, 1, 2
+
+_lib = None
+
+
+class D3MError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load (once) and return the ctypes handle of libd3m.so; raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise D3MError("deep3dmap_b200: %s not found -- build it with `python -m deep3dmap_b200.build` "
+                       "(there is no CPU / PyTorch fallback for this path)" % LIB_PATH)
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64, f32, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float, ctypes.c_size_t
+    L.d3m_version.restype = i32
+    L.d3m_last_error.restype = ctypes.c_char_p
+    L.d3m_device_count.restype = i32
+    for name in ("d3m_feats_nchw_to_nhwc", "d3m_feats_nhwc_to_nchw"):
+        f = getattr(L, name)
+        f.argtypes = [vp, vp, i64, i32, i32, i32, vp]
+        f.restype = i32
+    L.d3m_back_project_fwd_workspace.argtypes = [i64, i32, i32, i32]
+    L.d3m_back_project_fwd_workspace.restype = sz
+    L.d3m_back_project_fwd.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.d3m_back_project_fwd.restype = i32
+    L.d3m_back_project_bwd_workspace.argtypes = [i64, i32, i32, i32, i32, i32]
+    L.d3m_back_project_bwd_workspace.restype = sz
+    L.d3m_back_project_bwd.argtypes = [vp, i32, i64, vp, i32, f32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.d3m_back_project_bwd.restype = i32
+    L.d3m_tsdf_create.argtypes = [i32, i32, i32, vp, f32, f32, i32, ctypes.POINTER(vp)]
+    L.d3m_tsdf_create.restype = i32
+    L.d3m_tsdf_destroy.argtypes = [vp]
+    L.d3m_tsdf_destroy.restype = i32
+    L.d3m_tsdf_reset.argtypes = [vp, vp]
+    L.d3m_tsdf_reset.restype = i32
+    L.d3m_tsdf_integrate_host.argtypes = [vp, vp, vp, i32, i32, vp, vp, f32, i32, vp]
+    L.d3m_tsdf_integrate_host.restype = i32
+    L.d3m_tsdf_integrate_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp]
+    L.d3m_tsdf_integrate_device.restype = i32
+    L.d3m_tsdf_volumes.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(vp)]
+    L.d3m_tsdf_volumes.restype = i32
+    L.d3m_tsdf_download.argtypes = [vp, vp, vp, vp, vp]
+    L.d3m_tsdf_download.restype = i32
+    L.d3m_tsdf_last_launches.argtypes = [vp]
+    L.d3m_tsdf_last_launches.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().d3m_last_error()
+        raise D3MError("%s failed (code %d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def require_device():
+    if lib().d3m_device_count() <= 0:
+        raise D3MError("deep3dmap_b200: no CUDA device visible -- this path has no CPU fallback")

@@ -1,0 +1,559 @@
+// back_project forward for sm_100a: fused voxel->camera projection + in-frustum mask + bilinear gather
+// + masked multi-view mean + mean depth, then a deterministic two-kernel depth normalisation.
+// Replaces deep3dmap/core/voxel/back_project.py:23-84 of the reference (≈40 aten kernels per fragment).
+//
+// Work decomposition (one warp = one tile of `tv` consecutive voxels, no block-level sync at all):
+//   phase 1  lane <-> voxel: project the voxel into every view in order, keep count / z-sum in registers and
+//            push a 12-byte record {texel offset|corner flags, fx, fy} for every VALID view into the warp's
+//            shared-memory list (compacted, view order preserved).  Invalid samples cost nothing later.
+//   phase 2  lane group (G lanes, each R float4 = 4*G*R channels) <-> voxel: walk the voxel's record list;
+//            per record 4*R 128-bit channels-last texel loads per lane (one texel = C contiguous floats), the
+//            4-corner FMA chain in the aten order nw,ne,sw,se, then a separate add into the view sum.
+//   flush    the tile's (tv, C+1) rows are staged in shared memory and leave with ONE bulk async copy
+//            (cp.async.bulk, TMA engine) because (C+1)-float rows cannot be written with aligned vectors.
+// Arithmetic order is the oracle's (oracle/d3m_oracle.c) so features and counts are bit-identical to it.
+#include "d3m_common.cuh"
+
+namespace d3m {
+
+constexpr int kFwdWarps = 4;          // warps per CTA (each fully independent)
+constexpr int kMaxViewChunk = 16;     // views whose records are resident in smem at once
+constexpr unsigned kFull = 0xffffffffu;
+constexpr int kFlagX1 = 1 << 30;      // x0+1 < W
+constexpr int kFlagY1 = 1 << 31;      // y0+1 < H
+constexpr int kOffMask = (1 << 30) - 1;
+
+struct FwdParams {
+  const void* coords;
+  int64_t N;
+  const float* origin;
+  int B;
+  float vs;
+  const float* feats;
+  int V, C, H, W;
+  const float* KR;
+  float* out;
+  float* count;
+  float* zbar;
+  int* bidx;
+  unsigned int* counter;  // zeroed here for the stats kernel
+  int tv;
+  int vchunk;
+  int64_t num_tiles;
+  int per_warp_bytes;
+};
+
+__device__ __forceinline__ void bulk_store_tile(float* gdst, const float* ssrc, int bytes, int lane) {
+  // generic-proxy smem writes -> visible to the async proxy, then one lane hands the tile to the TMA engine
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gdst), "r"(saddr), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  __syncwarp();
+}
+
+// phase 1 for one chunk of views; returns the number of records pushed by this lane
+template <int KIND>
+__device__ __forceinline__ int push_records(const FwdParams& p, int b, float gx, float gy, float gz, int v0, int v1,
+                                            int lane, int* rec_off, float* rec_fx, float* rec_fy, float& zsum) {
+  int ccnt = 0;
+  if (b >= 0) {
+    const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
+    for (int v = v0; v < v1; ++v) {
+      float4 r0, r1, r2;
+      load_krcam(p.KR, v, p.B, b, r0, r1, r2);
+      const Sample s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
+      if (s.valid) {
+        int off = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
+        if (s.x0 + 1 < p.W) off |= kFlagX1;
+        if (s.y0 + 1 < p.H) off |= kFlagY1;
+        rec_off[ccnt * 32 + lane] = off;
+        rec_fx[ccnt * 32 + lane] = s.fx;
+        rec_fy[ccnt * 32 + lane] = s.fy;
+        ++ccnt;
+        zsum = __fadd_rn(zsum, s.z);
+      }
+    }
+  }
+  return ccnt;
+}
+
+__device__ __forceinline__ float corner_chain(float t00, float t01, float t10, float t11, float nw, float ne, float sw,
+                                              float se) {
+  // aten grid_sampler: out_acc = 0; out_acc += val*w for nw, ne, sw, se  (each contracted to one FMA)
+  return __fmaf_rn(t11, se, __fmaf_rn(t10, sw, __fmaf_rn(t01, ne, __fmul_rn(t00, nw))));
+}
+
+template <int KIND, int G, int R>
+__global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NG = 32 / G;  // lane groups per warp
+  const int g = lane / G, gl = lane % G;
+  const int C = p.C, C4 = C >> 2, C1 = C + 1;
+  unsigned char* wbase = smem + (size_t)warp * p.per_warp_bytes;
+  float* outs = reinterpret_cast<float*>(wbase);  // (tv, C+1), 16-byte aligned start
+  int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
+  float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
+  float* rec_fy = rec_fx + p.vchunk * 32;
+  const float4* __restrict__ feats4 = reinterpret_cast<const float4*>(p.feats);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.counter = 0u;
+
+  for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
+       tile += (int64_t)gridDim.x * kFwdWarps) {
+    const int64_t n0 = tile * p.tv;
+    const int64_t n = n0 + lane;
+    const bool active = lane < p.tv && n < p.N;
+    int b = -1;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (active) {
+      float cx, cy, cz;
+      b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
+      if (b >= 0) {
+        const float* o = p.origin + 3 * b;
+        voxel_world(cx, cy, cz, p.vs, __ldg(o), __ldg(o + 1), __ldg(o + 2), gx, gy, gz);
+      }
+    }
+    int cnt = 0;
+    float zsum = 0.0f;
+    for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
+      const int v1 = min(p.V, v0 + p.vchunk);
+      const bool first = (v0 == 0), last = (v1 == p.V);
+      const int ccnt = push_records<KIND>(p, b, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      cnt += ccnt;
+      __syncwarp();
+      for (int r = 0; r * NG < p.tv; ++r) {
+        const int j = r * NG + g;
+        const bool gvalid = (g < NG) && (j < p.tv);
+        int cj = __shfl_sync(kFull, ccnt, gvalid ? j : 0);
+        const int ctot = __shfl_sync(kFull, cnt, gvalid ? j : 0);
+        if (!gvalid) cj = 0;
+        const int kmax = __reduce_max_sync(kFull, cj);
+        float4 acc[R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          if (first || !gvalid) {
+            acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          } else {
+            const float* q = outs + j * C1 + (i * G + gl) * 4;
+            acc[i] = make_float4(q[0], q[1], q[2], q[3]);
+          }
+        }
+#pragma unroll 2
+        for (int k = 0; k < kmax; ++k) {
+          const bool on = k < cj;
+          const int jj = on ? j : 0;
+          const int of = rec_off[k * 32 + jj];
+          const float fx = on ? rec_fx[k * 32 + jj] : 0.0f, fy = on ? rec_fy[k * 32 + jj] : 0.0f;
+          const bool x1 = on && (of & kFlagX1), y1 = on && (of & kFlagY1);
+          const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy);
+          const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(fx, wy0), sw = __fmul_rn(wx0, fy),
+                      se = __fmul_rn(fx, fy);
+          const float4* base = feats4 + (int64_t)(of & kOffMask) * C4 + gl;
+          const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 t00[R], t01[R], t10[R], t11[R];
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            t00[i] = on ? __ldg(base + i * G) : zero;
+            t01[i] = x1 ? __ldg(base + C4 + i * G) : zero;
+            t10[i] = y1 ? __ldg(base + (int64_t)p.W * C4 + i * G) : zero;
+            t11[i] = (x1 && y1) ? __ldg(base + (int64_t)(p.W + 1) * C4 + i * G) : zero;
+          }
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            acc[i].x = __fadd_rn(acc[i].x, corner_chain(t00[i].x, t01[i].x, t10[i].x, t11[i].x, nw, ne, sw, se));
+            acc[i].y = __fadd_rn(acc[i].y, corner_chain(t00[i].y, t01[i].y, t10[i].y, t11[i].y, nw, ne, sw, se));
+            acc[i].z = __fadd_rn(acc[i].z, corner_chain(t00[i].z, t01[i].z, t10[i].z, t11[i].z, nw, ne, sw, se));
+            acc[i].w = __fadd_rn(acc[i].w, corner_chain(t00[i].w, t01[i].w, t10[i].w, t11[i].w, nw, ne, sw, se));
+          }
+        }
+        if (gvalid) {
+          const float div = (float)max(ctot, 1);
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            float4 a = acc[i];
+            if (last) {  // features /= max(count,1)   (back_project.py:69-72)
+              a.x = __fdiv_rn(a.x, div); a.y = __fdiv_rn(a.y, div);
+              a.z = __fdiv_rn(a.z, div); a.w = __fdiv_rn(a.w, div);
+            }
+            float* q = outs + j * C1 + (i * G + gl) * 4;
+            q[0] = a.x; q[1] = a.y; q[2] = a.z; q[3] = a.w;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // per-voxel scalars: count, mean depth (normalised later), fragment index
+    if (lane < p.tv) {
+      const float zb = __fdiv_rn(zsum, (float)max(cnt, 1));
+      outs[lane * C1 + C] = zb;
+      if (active) {
+        p.count[n] = (float)cnt;
+        p.zbar[n] = zb;
+        p.bidx[n] = b;
+      }
+    }
+    const int rows = (int)min((int64_t)p.tv, p.N - n0);
+    const int bytes = rows * C1 * 4;
+    float* gdst = p.out + n0 * C1;
+    if ((bytes & 15) == 0) {
+      bulk_store_tile(gdst, outs, bytes, lane);
+    } else {
+      __syncwarp();
+      for (int i = lane; i < rows * C1; i += 32) gdst[i] = outs[i];
+      __syncwarp();
+    }
+  }
+}
+
+// Any channel count up to 256: the warp takes one voxel at a time, lanes stride over channels (scalar loads).
+constexpr int kGenericMaxR = 8;
+template <int KIND>
+__global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const FwdParams p) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int C = p.C, C1 = C + 1;
+  unsigned char* wbase = smem + (size_t)warp * p.per_warp_bytes;
+  float* outs = reinterpret_cast<float*>(wbase);
+  int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
+  float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
+  float* rec_fy = rec_fx + p.vchunk * 32;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *p.counter = 0u;
+
+  for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
+       tile += (int64_t)gridDim.x * kFwdWarps) {
+    const int64_t n0 = tile * p.tv;
+    const int64_t n = n0 + lane;
+    const bool active = lane < p.tv && n < p.N;
+    int b = -1;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (active) {
+      float cx, cy, cz;
+      b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
+      if (b >= 0) {
+        const float* o = p.origin + 3 * b;
+        voxel_world(cx, cy, cz, p.vs, __ldg(o), __ldg(o + 1), __ldg(o + 2), gx, gy, gz);
+      }
+    }
+    int cnt = 0;
+    float zsum = 0.0f;
+    for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
+      const int v1 = min(p.V, v0 + p.vchunk);
+      const bool first = (v0 == 0), last = (v1 == p.V);
+      const int ccnt = push_records<KIND>(p, b, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      cnt += ccnt;
+      __syncwarp();
+      for (int j = 0; j < p.tv; ++j) {
+        const int cj = __shfl_sync(kFull, ccnt, j);
+        const int ctot = __shfl_sync(kFull, cnt, j);
+        float acc[kGenericMaxR];
+#pragma unroll
+        for (int i = 0; i < kGenericMaxR; ++i) {
+          const int c = lane + 32 * i;
+          acc[i] = (first || c >= C) ? 0.0f : outs[j * C1 + c];
+        }
+        for (int k = 0; k < cj; ++k) {
+          const int of = rec_off[k * 32 + j];
+          const float fx = rec_fx[k * 32 + j], fy = rec_fy[k * 32 + j];
+          const bool x1 = of & kFlagX1, y1 = of & kFlagY1;
+          const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy);
+          const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(fx, wy0), sw = __fmul_rn(wx0, fy),
+                      se = __fmul_rn(fx, fy);
+          const float* base = p.feats + (int64_t)(of & kOffMask) * C;
+#pragma unroll
+          for (int i = 0; i < kGenericMaxR; ++i) {
+            const int c = lane + 32 * i;
+            if (c < C) {
+              const float t00 = __ldg(base + c);
+              const float t01 = x1 ? __ldg(base + C + c) : 0.0f;
+              const float t10 = y1 ? __ldg(base + (int64_t)p.W * C + c) : 0.0f;
+              const float t11 = (x1 && y1) ? __ldg(base + (int64_t)(p.W + 1) * C + c) : 0.0f;
+              acc[i] = __fadd_rn(acc[i], corner_chain(t00, t01, t10, t11, nw, ne, sw, se));
+            }
+          }
+        }
+        const float div = (float)max(ctot, 1);
+#pragma unroll
+        for (int i = 0; i < kGenericMaxR; ++i) {
+          const int c = lane + 32 * i;
+          if (c < C) outs[j * C1 + c] = last ? __fdiv_rn(acc[i], div) : acc[i];
+        }
+      }
+      __syncwarp();
+    }
+    if (lane < p.tv) {
+      const float zb = __fdiv_rn(zsum, (float)max(cnt, 1));
+      outs[lane * C1 + C] = zb;
+      if (active) {
+        p.count[n] = (float)cnt;
+        p.zbar[n] = zb;
+        p.bidx[n] = b;
+      }
+    }
+    const int rows = (int)min((int64_t)p.tv, p.N - n0);
+    const int bytes = rows * C1 * 4;
+    float* gdst = p.out + n0 * C1;
+    if ((bytes & 15) == 0) {
+      bulk_store_tile(gdst, outs, bytes, lane);
+    } else {
+      __syncwarp();
+      for (int i = lane; i < rows * C1; i += 32) gdst[i] = outs[i];
+      __syncwarp();
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depth normalisation (back_project.py:77-80): per fragment, over voxels with mean depth > 0,
+//   mu = mean(z), sd = ||z - mu||_2 + 1e-5, zn = (z - mu)/sd, zn[z<=0] = 0.
+// Deterministic: fixed chunk->CTA assignment, fixed-shape fp64 trees, the last CTA (ticket counter)
+// folds the per-chunk partials in chunk order.  Sum(z-mu)^2 is evaluated as Sz2 - 2 mu Sz + n mu^2 in
+// fp64 (relative error ~1e-15 here), so one pass over the compact z array suffices.
+// ------------------------------------------------------------------------------------------------
+constexpr int kStatsThreads = 256;
+constexpr int kStatsChunk = 4096;
+constexpr int kStatsMaxChunks = 2048;
+
+struct StatsParams {
+  const float* zbar;
+  const int* bidx;
+  int64_t N;
+  int B;
+  int nchunks;
+  int64_t chunk;
+  double* partial;  // (nchunks, B, 3)
+  float* stats;     // (B, 2): mean, sd
+  unsigned int* counter;
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
+  return v;
+}
+
+__global__ void __launch_bounds__(kStatsThreads) bp_stats_kernel(const StatsParams p) {
+  __shared__ double red[3][kStatsThreads / 32];
+  __shared__ int s_bmin, s_bmax;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t i0 = (int64_t)blockIdx.x * p.chunk, i1 = min(p.N, i0 + p.chunk);
+  if (tid == 0) { s_bmin = 0x7fffffff; s_bmax = -1; }
+  __syncthreads();
+  int bmin = 0x7fffffff, bmax = -1;
+  for (int64_t i = i0 + tid; i < i1; i += kStatsThreads) {
+    const int b = p.bidx[i];
+    if (b >= 0) { bmin = min(bmin, b); bmax = max(bmax, b); }
+  }
+  bmin = __reduce_min_sync(kFull, bmin);
+  bmax = __reduce_max_sync(kFull, bmax);
+  if (lane == 0) { atomicMin(&s_bmin, bmin); atomicMax(&s_bmax, bmax); }
+  __syncthreads();
+  bmin = s_bmin; bmax = s_bmax;
+  double* my = p.partial + (size_t)blockIdx.x * p.B * 3;
+  for (int b = tid; b < p.B; b += kStatsThreads)
+    if (b < bmin || b > bmax) { my[b * 3 + 0] = 0.0; my[b * 3 + 1] = 0.0; my[b * 3 + 2] = 0.0; }
+  for (int b = bmin; b <= bmax; ++b) {
+    double s = 0.0, s2 = 0.0, c = 0.0;
+    for (int64_t i = i0 + tid; i < i1; i += kStatsThreads) {
+      const float z = p.zbar[i];
+      if (p.bidx[i] == b && z > 0.0f) { s += (double)z; s2 += (double)z * (double)z; c += 1.0; }
+    }
+    s = warp_sum(s); s2 = warp_sum(s2); c = warp_sum(c);
+    if (lane == 0) { red[0][warp] = s; red[1][warp] = s2; red[2][warp] = c; }
+    __syncthreads();
+    if (tid == 0) {
+      double a = 0.0, a2 = 0.0, ac = 0.0;
+      for (int w = 0; w < kStatsThreads / 32; ++w) { a += red[0][w]; a2 += red[1][w]; ac += red[2][w]; }
+      my[b * 3 + 0] = a; my[b * 3 + 1] = a2; my[b * 3 + 2] = ac;
+    }
+    __syncthreads();
+  }
+  // ticket: the last CTA to arrive folds all partials in chunk order (order-independent of who is last)
+  __threadfence();
+  if (tid == 0) s_last = (atomicAdd(p.counter, 1u) == (unsigned)(gridDim.x - 1));
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int b = tid; b < p.B; b += kStatsThreads) {
+    double s = 0.0, s2 = 0.0, c = 0.0;
+    for (int k = 0; k < p.nchunks; ++k) {
+      const volatile double* q = p.partial + ((size_t)k * p.B + b) * 3;
+      s += q[0]; s2 += q[1]; c += q[2];
+    }
+    float mean, sd;
+    if (c > 0.0) {
+      mean = (float)(s / c);
+      const double m = (double)mean;
+      double ssq = s2 - 2.0 * m * s + c * m * m;
+      if (ssq < 0.0) ssq = 0.0;
+      sd = __fadd_rn((float)sqrt(ssq), 1e-5f);
+    } else {
+      mean = __int_as_float(0x7fc00000);  // mean of an empty set is NaN in the reference; never used (z<=0 -> 0)
+      sd = 1e-5f;
+    }
+    p.stats[2 * b] = mean;
+    p.stats[2 * b + 1] = sd;
+  }
+}
+
+__global__ void __launch_bounds__(256) bp_normalise_kernel(const float* __restrict__ zbar, const int* __restrict__ bidx,
+                                                           const float* __restrict__ stats, float* __restrict__ out,
+                                                           int64_t N, int C1) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int b = bidx[n];
+  const float z = zbar[n];
+  float zn = 0.0f;
+  if (b >= 0 && z > 0.0f) zn = __fdiv_rn(__fsub_rn(z, stats[2 * b]), stats[2 * b + 1]);
+  out[n * C1 + (C1 - 1)] = zn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct FwdWs {
+  size_t zbar, bidx, partial, stats, counter, total;
+  int nchunks;
+  int64_t chunk;
+};
+
+static FwdWs fwd_ws_layout(int64_t N, int B) {
+  FwdWs w;
+  int64_t nch = (N + kStatsChunk - 1) / kStatsChunk;
+  if (nch < 1) nch = 1;
+  int64_t chunk = kStatsChunk;
+  if (nch > kStatsMaxChunks) {
+    chunk = (N + kStatsMaxChunks - 1) / kStatsMaxChunks;
+    nch = (N + chunk - 1) / chunk;
+  }
+  w.nchunks = (int)nch;
+  w.chunk = chunk;
+  size_t o = 0;
+  w.zbar = o; o = align_up(o + sizeof(float) * (size_t)(N > 0 ? N : 1), 256);
+  w.bidx = o; o = align_up(o + sizeof(int) * (size_t)(N > 0 ? N : 1), 256);
+  w.partial = o; o = align_up(o + sizeof(double) * 3 * (size_t)nch * (size_t)(B > 0 ? B : 1), 256);
+  w.stats = o; o = align_up(o + sizeof(float) * 2 * (size_t)(B > 0 ? B : 1), 256);
+  w.counter = o; o = align_up(o + 256, 256);
+  w.total = o;
+  return w;
+}
+
+typedef void (*fwd_kernel_t)(const FwdParams);
+
+template <int KIND>
+static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
+  // (G lanes x R float4 per lane) = C/4 chunks; prefer the widest group that keeps >= 30/32 lanes busy
+  G = 0; R = 0;
+  if (C % 4 != 0) return nullptr;
+  const int q = C / 4;
+#define D3M_FWD_CASE(g, r)            \
+  if (q == (g) * (r)) {               \
+    G = (g); R = (r);                 \
+    return bp_fwd_kernel<KIND, g, r>; \
+  }
+  D3M_FWD_CASE(6, 1)    // C = 24  (level 2)
+  D3M_FWD_CASE(10, 1)   // C = 40  (level 1)
+  D3M_FWD_CASE(10, 2)   // C = 80  (level 0)
+  D3M_FWD_CASE(4, 1)    // C = 16
+  D3M_FWD_CASE(8, 1)    // C = 32
+  D3M_FWD_CASE(16, 1)   // C = 64
+  D3M_FWD_CASE(8, 3)    // C = 96
+  D3M_FWD_CASE(16, 2)   // C = 128
+  D3M_FWD_CASE(2, 1)    // C = 8
+  D3M_FWD_CASE(3, 1)    // C = 12
+  D3M_FWD_CASE(5, 1)    // C = 20
+#undef D3M_FWD_CASE
+  return nullptr;
+}
+
+template <int KIND>
+static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
+  FwdParams p = p0;
+  int G, R;
+  fwd_kernel_t k = pick_fwd_kernel<KIND>(p.C, G, R);
+  if (!k) {
+    D3M_REQUIRE(p.C <= 32 * kGenericMaxR, D3M_ERR_ARG, "back_project: C=%d unsupported (C%%4!=0 needs C<=%d)", p.C,
+                32 * kGenericMaxR);
+    k = bp_fwd_generic_kernel<KIND>;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // voxels per warp tile: 32 for large N; shrink for small N so every SM still gets several warps
+  int tv = 32;
+  while (tv > 8 && (p.N + tv - 1) / tv < (int64_t)sms * 16) tv >>= 1;
+  p.tv = tv;
+  p.vchunk = p.V < kMaxViewChunk ? p.V : kMaxViewChunk;
+  p.num_tiles = (p.N + tv - 1) / tv;
+  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)3 * p.vchunk * 32 * 4, 16);
+  const size_t smem = (size_t)p.per_warp_bytes * kFwdWarps;
+  D3M_REQUIRE(smem <= 200 * 1024, D3M_ERR_ARG, "back_project: C=%d needs %zu B shared memory per CTA", p.C, smem);
+  D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t ctas = (p.num_tiles + kFwdWarps - 1) / kFwdWarps;
+  const int64_t cap = (int64_t)sms * 32;
+  if (ctas > cap) ctas = cap;
+  if (ctas < 1) ctas = 1;
+  k<<<(unsigned)ctas, kFwdWarps * 32, smem, stream>>>(p);
+  D3M_CUDA_CHECK(cudaGetLastError());
+  return D3M_OK;
+}
+
+}  // namespace d3m
+
+using namespace d3m;
+
+extern "C" size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C) {
+  (void)V; (void)C;
+  if (N < 0 || B < 1) return 0;
+  return fwd_ws_layout(N, B).total;
+}
+
+extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                    float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
+                                    const float* KRcam, float* out, float* count, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "back_project: no CUDA device (there is no CPU fallback)");
+  D3M_REQUIRE(N >= 0 && B >= 1 && V >= 1 && C >= 1 && H >= 2 && W >= 2, D3M_ERR_ARG,
+              "back_project: bad sizes N=%lld B=%d V=%d C=%d H=%d W=%d", (long long)N, B, V, C, H, W);
+  D3M_REQUIRE(coords_kind >= 0 && coords_kind <= 2, D3M_ERR_ARG, "back_project: coords_kind=%d", coords_kind);
+  D3M_REQUIRE((int64_t)V * B * H * W < (1ll << 30), D3M_ERR_ARG, "back_project: V*B*H*W must be < 2^30 texels");
+  if (N == 0) return D3M_OK;
+  D3M_REQUIRE(coords && origin && feats_nhwc && KRcam && out && count && workspace, D3M_ERR_ARG,
+              "back_project: NULL pointer");
+  D3M_REQUIRE(aligned16(coords) && aligned16(feats_nhwc) && aligned16(KRcam) && aligned16(out) &&
+                  aligned16(workspace),
+              D3M_ERR_ALIGN, "back_project: coords/feats/KRcam/out/workspace must be 16-byte aligned");
+  const FwdWs w = fwd_ws_layout(N, B);
+  D3M_REQUIRE(workspace_bytes >= w.total, D3M_ERR_WORKSPACE, "back_project: workspace %zu < %zu", workspace_bytes,
+              w.total);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
+  FwdParams p;
+  p.coords = coords; p.N = N; p.origin = origin; p.B = B; p.vs = voxel_size;
+  p.feats = feats_nhwc; p.V = V; p.C = C; p.H = H; p.W = W; p.KR = KRcam;
+  p.out = out; p.count = count;
+  p.zbar = reinterpret_cast<float*>(ws + w.zbar);
+  p.bidx = reinterpret_cast<int*>(ws + w.bidx);
+  p.counter = reinterpret_cast<unsigned int*>(ws + w.counter);
+  int rc;
+  if (coords_kind == D3M_COORDS_F32) rc = launch_fwd<D3M_COORDS_F32>(p, stream);
+  else if (coords_kind == D3M_COORDS_I64) rc = launch_fwd<D3M_COORDS_I64>(p, stream);
+  else rc = launch_fwd<D3M_COORDS_I32>(p, stream);
+  if (rc != D3M_OK) return rc;
+  StatsParams sp;
+  sp.zbar = p.zbar; sp.bidx = p.bidx; sp.N = N; sp.B = B; sp.nchunks = w.nchunks; sp.chunk = w.chunk;
+  sp.partial = reinterpret_cast<double*>(ws + w.partial);
+  sp.stats = reinterpret_cast<float*>(ws + w.stats);
+  sp.counter = p.counter;
+  bp_stats_kernel<<<w.nchunks, kStatsThreads, 0, stream>>>(sp);
+  D3M_CUDA_CHECK(cudaGetLastError());
+  bp_normalise_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(p.zbar, p.bidx, sp.stats, out, N, C + 1);
+  D3M_CUDA_CHECK(cudaGetLastError());
+  return D3M_OK;
+}

@@ -1,0 +1,79 @@
+// libd3m core: error reporting, device probe, and the NCHW <-> NHWC relayout of the per-view feature maps.
+#include <stdarg.h>
+#include <string.h>
+
+#include "d3m_common.cuh"
+
+namespace d3m {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what) {
+  set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
+  return D3M_ERR_CUDA + (int)e;
+}
+
+// (n_maps, A, Bn) -> (n_maps, Bn, A) through a padded 32x32 shared-memory tile: both sides coalesced.
+__global__ void __launch_bounds__(256) transpose_maps_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             int A, int Bn) {
+  __shared__ float tile[32][33];
+  const int64_t map = blockIdx.z;
+  const float* s = src + map * (int64_t)A * Bn;
+  float* d = dst + map * (int64_t)A * Bn;
+  const int b0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int a = a0 + ty + i, b = b0 + tx;
+    if (a < A && b < Bn) tile[ty + i][tx] = __ldg(s + (int64_t)a * Bn + b);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int b = b0 + ty + i, a = a0 + tx;
+    if (a < A && b < Bn) d[(int64_t)b * A + a] = tile[tx][ty + i];
+  }
+}
+
+static int transpose_maps(const float* src, float* dst, int64_t n_maps, int A, int Bn, cudaStream_t stream) {
+  D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "relayout: no CUDA device (there is no CPU fallback)");
+  D3M_REQUIRE(src && dst && n_maps >= 0 && A >= 1 && Bn >= 1, D3M_ERR_ARG, "relayout: bad arguments");
+  if (n_maps == 0) return D3M_OK;
+  for (int64_t m0 = 0; m0 < n_maps; m0 += 65535) {
+    const unsigned nz = (unsigned)((n_maps - m0) < 65535 ? (n_maps - m0) : 65535);
+    dim3 grid((Bn + 31) / 32, (A + 31) / 32, nz);
+    transpose_maps_kernel<<<grid, 256, 0, stream>>>(src + m0 * (int64_t)A * Bn, dst + m0 * (int64_t)A * Bn, A, Bn);
+    D3M_CUDA_CHECK(cudaGetLastError());
+  }
+  return D3M_OK;
+}
+
+}  // namespace d3m
+
+extern "C" int d3m_version(void) { return D3M_VERSION; }
+
+extern "C" const char* d3m_last_error(void) { return d3m::g_err; }
+
+extern "C" int d3m_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+extern "C" int d3m_feats_nchw_to_nhwc(const float* src, float* dst, int64_t n_maps, int C, int H, int W, void* stream) {
+  return d3m::transpose_maps(src, dst, n_maps, C, H * W, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int d3m_feats_nhwc_to_nchw(const float* src, float* dst, int64_t n_maps, int C, int H, int W, void* stream) {
+  return d3m::transpose_maps(src, dst, n_maps, H * W, C, static_cast<cudaStream_t>(stream));
+}

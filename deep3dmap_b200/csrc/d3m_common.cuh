@@ -1,0 +1,109 @@
+// Shared device/host helpers of libd3m (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/d3m.h"
+
+namespace d3m {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define D3M_CUDA_CHECK(expr)                                   \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::d3m::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define D3M_REQUIRE(cond, code, ...)   \
+  do {                                 \
+    if (!(cond)) {                     \
+      ::d3m::set_error(__VA_ARGS__);   \
+      return (code);                   \
+    }                                  \
+  } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+__host__ __device__ static inline int align_up_dev(int x) { return (x + 15) & ~15; }
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ------------------------------------------------------------------------------------------------
+// coords row -> (fragment index or -1, xyz as float).  back_project.py:29-30: a row belongs to
+// fragment b iff coords[:,0] == b.
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ int load_coord(const void* __restrict__ coords, int64_t n, int B, float& x, float& y,
+                                          float& z) {
+  int b = -1;
+  if (KIND == D3M_COORDS_F32) {
+    const float4 c = __ldg(reinterpret_cast<const float4*>(coords) + n);
+    if (c.x >= 0.0f && c.x < (float)B && c.x == floorf(c.x)) b = (int)c.x;
+    x = c.y; y = c.z; z = c.w;
+  } else if (KIND == D3M_COORDS_I64) {
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(coords) + 2 * n);
+    const longlong2 c = __ldg(reinterpret_cast<const longlong2*>(coords) + 2 * n + 1);
+    if (a.x >= 0 && a.x < (long long)B) b = (int)a.x;
+    x = (float)a.y; y = (float)c.x; z = (float)c.y;
+  } else {
+    const int4 c = __ldg(reinterpret_cast<const int4*>(coords) + n);
+    if (c.x >= 0 && c.x < B) b = c.x;
+    x = (float)c.y; y = (float)c.z; z = (float)c.w;
+  }
+  return b;
+}
+
+// ------------------------------------------------------------------------------------------------
+// One voxel-view projection with the exact fp32 rounding sequence of the reference
+// (back_project.py:37-51 + aten grid_sampler un-normalisation, align_corners=True):
+//   grid = coords*vs + origin (mul, add) ; p_r = fma chain over k=0..3 (== torch bmm, K=4)
+//   u = p0/p2 ; nx = (2u)/(W-1) - 1 ; valid = |nx|<=1 & |ny|<=1 & p2>0
+//   ix = ((nx+1)/2)*(W-1) ; x0 = floor(ix) ; fx = ix-x0 (exact)
+// Explicit _rn intrinsics keep nvcc from contracting anything.
+// ------------------------------------------------------------------------------------------------
+struct Sample {
+  float z, fx, fy;
+  int x0, y0;
+  bool valid;
+};
+
+__device__ __forceinline__ void voxel_world(float cx, float cy, float cz, float vs, float ox, float oy, float oz,
+                                            float& gx, float& gy, float& gz) {
+  gx = __fadd_rn(__fmul_rn(cx, vs), ox);
+  gy = __fadd_rn(__fmul_rn(cy, vs), oy);
+  gz = __fadd_rn(__fmul_rn(cz, vs), oz);
+}
+
+// P: first three rows of the 4x4 matrix, row-major (12 floats used of 16)
+__device__ __forceinline__ Sample project(float gx, float gy, float gz, const float4 r0, const float4 r1,
+                                          const float4 r2, float wm1, float hm1) {
+  Sample s;
+  const float p0 = __fadd_rn(__fmaf_rn(r0.z, gz, __fmaf_rn(r0.y, gy, __fmul_rn(r0.x, gx))), r0.w);
+  const float p1 = __fadd_rn(__fmaf_rn(r1.z, gz, __fmaf_rn(r1.y, gy, __fmul_rn(r1.x, gx))), r1.w);
+  const float p2 = __fadd_rn(__fmaf_rn(r2.z, gz, __fmaf_rn(r2.y, gy, __fmul_rn(r2.x, gx))), r2.w);
+  const float u = __fdiv_rn(p0, p2);
+  const float v = __fdiv_rn(p1, p2);
+  const float nx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, u), wm1), 1.0f);
+  const float ny = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), hm1), 1.0f);
+  s.z = p2;
+  s.valid = (fabsf(nx) <= 1.0f) && (fabsf(ny) <= 1.0f) && (p2 > 0.0f);
+  const float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.0f), 0.5f), wm1);
+  const float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.0f), 0.5f), hm1);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  s.x0 = (int)x0f;
+  s.y0 = (int)y0f;
+  s.fx = __fsub_rn(ix, x0f);
+  s.fy = __fsub_rn(iy, y0f);
+  return s;
+}
+
+__device__ __forceinline__ void load_krcam(const float* __restrict__ KR, int v, int B, int b, float4& r0, float4& r1,
+                                           float4& r2) {
+  const float4* p = reinterpret_cast<const float4*>(KR) + ((int64_t)v * B + b) * 4;
+  r0 = __ldg(p);
+  r1 = __ldg(p + 1);
+  r2 = __ldg(p + 2);
+}
+
+}  // namespace d3m

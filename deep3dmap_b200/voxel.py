@@ -1,0 +1,153 @@
+"""Drop-in for `deep3dmap/core/voxel/back_project.py:5-84` of the reference.
+
+    volume, count = back_project(coords, origin, voxel_size, feats, KRcam)
+
+Same signature, argument meaning and return layout as the reference function; the work is done by
+the hand-written sm_100a kernels of `libd3m.so` (forward: `csrc/back_project_fwd.cu`, deterministic
+backward w.r.t. `feats`: `csrc/back_project_bwd.cu`).  PyTorch only provides device memory, the
+current stream and the autograd hook.  There is no fallback path: CPU tensors raise.
+"""
+import torch
+
+from . import _lib
+
+_COORD_KIND = {torch.float32: _lib.COORDS_F32, torch.int64: _lib.COORDS_I64, torch.int32: _lib.COORDS_I32}
+
+# gradient layout returned to autograd: "nchw" = contiguous (V,B,C,H,W) like the reference's;
+# "view" = zero-copy permuted view of the kernel's channels-last buffer
+GRAD_LAYOUT = "nchw"
+
+
+def _ptr(t):
+    return t.data_ptr() if t is not None and t.numel() > 0 else None
+
+
+def _stream(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def feats_to_channels_last(feats):
+    """(V,B,C,H,W) -> channels-last storage (V,B,H,W,C); zero-copy when `feats` already is a permuted view."""
+    if feats.dim() != 5:
+        raise ValueError("feats must be (n_views, batch, C, H, W)")
+    nhwc_view = feats.permute(0, 1, 3, 4, 2)
+    if nhwc_view.is_contiguous():
+        return nhwc_view
+    f = feats.contiguous()
+    V, B, C, H, W = f.shape
+    out = torch.empty((V, B, H, W, C), dtype=torch.float32, device=f.device)
+    if f.numel():
+        rc = _lib.lib().d3m_feats_nchw_to_nhwc(f.data_ptr(), out.data_ptr(), V * B, C, H, W, _stream(f.device))
+        _lib.check(rc, "d3m_feats_nchw_to_nhwc")
+    return out
+
+
+def feats_to_nchw(g_nhwc):
+    """(V,B,H,W,C) channels-last storage -> contiguous (V,B,C,H,W)."""
+    V, B, H, W, C = g_nhwc.shape
+    out = torch.empty((V, B, C, H, W), dtype=torch.float32, device=g_nhwc.device)
+    if g_nhwc.numel():
+        rc = _lib.lib().d3m_feats_nhwc_to_nchw(g_nhwc.data_ptr(), out.data_ptr(), V * B, C, H, W,
+                                               _stream(g_nhwc.device))
+        _lib.check(rc, "d3m_feats_nhwc_to_nchw")
+    return out
+
+
+def _prep_small(coords, origin, KRcam, device):
+    if coords.dim() != 2 or coords.shape[1] != 4:
+        raise ValueError("coords must be (num_voxels, 4) [batch, x, y, z]")
+    if coords.dtype not in _COORD_KIND:
+        coords = coords.float()
+    coords = coords.contiguous()
+    origin = origin.to(device=device, dtype=torch.float32).contiguous()
+    KRcam = KRcam.to(device=device, dtype=torch.float32).contiguous()
+    return coords, origin, KRcam
+
+
+def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam):
+    """Kernel-level forward on channels-last maps (V,B,H,W,C).  Returns (volume (N,C+1), count (N,))."""
+    L = _lib.lib()
+    dev = feats_nhwc.device
+    V, B, H, W, C = feats_nhwc.shape
+    N = coords.shape[0]
+    if origin.shape != (B, 3) or KRcam.shape != (V, B, 4, 4):
+        raise ValueError("origin must be (B,3) and KRcam (V,B,4,4) for feats (V,B,C,H,W)")
+    out = torch.empty((N, C + 1), dtype=torch.float32, device=dev)
+    count = torch.empty((N,), dtype=torch.float32, device=dev)
+    if N == 0:
+        return out, count
+    ws_bytes = L.d3m_back_project_fwd_workspace(N, B, V, C)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.d3m_back_project_fwd(coords.data_ptr(), _COORD_KIND[coords.dtype], N, origin.data_ptr(), B,
+                                    float(voxel_size), feats_nhwc.data_ptr(), V, C, H, W, KRcam.data_ptr(),
+                                    out.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev))
+    _lib.check(rc, "d3m_back_project_fwd")
+    return out, count
+
+
+def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, grad_out):
+    """Kernel-level backward: grad_out (N,C+1) -> grad of the channels-last maps (V,B,H,W,C)."""
+    L = _lib.lib()
+    dev = grad_out.device
+    V, B, H, W, C = feats_shape_nhwc
+    N = coords.shape[0]
+    grad = torch.empty((V, B, H, W, C), dtype=torch.float32, device=dev)
+    if grad.numel() == 0:
+        return grad
+    ws_bytes = L.d3m_back_project_bwd_workspace(N, B, V, C, H, W)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.d3m_back_project_bwd(_ptr(coords), _COORD_KIND[coords.dtype], N, _ptr(origin), B, float(voxel_size),
+                                    V, C, H, W, _ptr(KRcam), _ptr(grad_out), grad.data_ptr(), ws.data_ptr(),
+                                    ws_bytes, _stream(dev))
+    _lib.check(rc, "d3m_back_project_bwd")
+    return grad
+
+
+class _BackProject(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, coords, origin, voxel_size, KRcam):
+        if not feats.is_cuda:
+            raise _lib.D3MError("back_project: feats must live on a CUDA device (no CPU fallback in this build)")
+        _lib.require_device()
+        if feats.dtype != torch.float32:
+            feats = feats.float()
+        dev = feats.device
+        coords = coords.to(dev)
+        coords, origin, KRcam = _prep_small(coords, origin, KRcam, dev)
+        nhwc = feats_to_channels_last(feats)
+        out, count = back_project_forward(coords, origin, voxel_size, nhwc, KRcam)
+        ctx.save_for_backward(coords, origin, KRcam)
+        ctx.voxel_size = float(voxel_size)
+        ctx.nhwc_shape = tuple(nhwc.shape)
+        ctx.mark_non_differentiable(count)
+        return out, count
+
+    @staticmethod
+    def backward(ctx, grad_vol, grad_count):
+        coords, origin, KRcam = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return None, None, None, None, None
+        g = grad_vol.contiguous().float()
+        grad_nhwc = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g)
+        if GRAD_LAYOUT == "view":
+            grad = grad_nhwc.permute(0, 1, 4, 2, 3)
+        else:
+            grad = feats_to_nchw(grad_nhwc)
+        return grad, None, None, None, None
+
+
+def back_project(coords, origin, voxel_size, feats, KRcam):
+    '''
+    Unproject the image fetures to form a 3D (sparse) feature volume  (reference back_project.py:5-22)
+
+    :param coords: coordinates of voxels, dim: (num of voxels, 4) (4 : batch ind, x, y, z); float32, int64 or int32
+    :param origin: origin of the partial voxel volume (xyz position of voxel (0, 0, 0)), dim: (batch size, 3)
+    :param voxel_size: floats specifying the size of a voxel
+    :param feats: image features, dim: (num of views, batch size, C, H, W)
+    :param KRcam: projection matrix, dim: (num of views, batch size, 4, 4)
+    :return: feature_volume_all: 3D feature volumes, dim: (num of voxels, c + 1)
+    :return: count: number of times each voxel can be seen, dim: (num of voxels,)
+    '''
+    return _BackProject.apply(feats, coords, origin, voxel_size, KRcam)

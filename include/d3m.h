@@ -1,0 +1,138 @@
+/*
+ * d3m.h -- C ABI of the B200-native NeuralRecon lifting hot path (libd3m.so).
+ *
+ * Drop-in boundary for two reference entry points of achao2013/deep3dmap (paths relative to the
+ * reference tree):
+ *   back_project(coords, origin, voxel_size, feats, KRcam)      deep3dmap/core/voxel/back_project.py:5-84
+ *   TSDFVolume.__init__/integrate/get_volume                    deep3dmap/core/tsdf/tsdf_volume.py:14-307
+ *   TSDFVolumeTorch.integrate (dataloader variant)              deep3dmap/core/tsdf/tsdf_volume.py:437-574
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / CUDA-runtime types in the signatures.  `stream` is a
+ *     cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`.
+ *   - every call returns 0 on success; non-zero = D3M_ERR_* (argument errors) or 1000 + cudaError_t.
+ *     `d3m_last_error()` returns a thread-local, human-readable message for the last failure.
+ *   - calls are asynchronous on `stream` unless stated otherwise; they never synchronise the device
+ *     except `d3m_tsdf_download` and `d3m_tsdf_create/destroy`.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails with
+ *     D3M_ERR_NO_DEVICE.
+ */
+#ifndef D3M_H_
+#define D3M_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D3M_VERSION 100
+
+enum {
+  D3M_OK = 0,
+  D3M_ERR_ARG = 1,        /* bad shape / NULL pointer / unsupported size */
+  D3M_ERR_WORKSPACE = 2,  /* workspace too small */
+  D3M_ERR_NO_DEVICE = 3,
+  D3M_ERR_ALIGN = 4,      /* pointer not 16-byte aligned */
+  D3M_ERR_CUDA = 1000     /* + cudaError_t */
+};
+
+/* dtype of the (N,4) [batch,x,y,z] coordinate rows.  The reference passes float32 from
+ * generate_grid (core/voxel/generate_grids.py:9) and int64 when coords come from torch.nonzero
+ * (models/modulars/gru_fusion.py:294-300); int32 is an extension for >2^24-voxel scenes. */
+enum { D3M_COORDS_F32 = 0, D3M_COORDS_I64 = 1, D3M_COORDS_I32 = 2 };
+
+int d3m_version(void);
+const char* d3m_last_error(void);
+/* number of CUDA devices visible (0 when none / driver missing); never fails */
+int d3m_device_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Feature-map layout.  The kernels read / write per-view maps channels-last: (V,B,H,W,C) so that one
+ * texel is C contiguous floats (128-bit loads).  The reference hands over (V,B,C,H,W) as produced
+ * by torch.stack (models/neucon_network.py:128); these two kernels convert n_maps = V*B maps.
+ * ------------------------------------------------------------------------------------------- */
+int d3m_feats_nchw_to_nhwc(const float* src, float* dst, int64_t n_maps, int C, int H, int W, void* stream);
+int d3m_feats_nhwc_to_nchw(const float* src, float* dst, int64_t n_maps, int C, int H, int W, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * back_project forward  (replaces back_project.py:23-84)
+ *   coords      (N,4) rows [batch, x, y, z] in voxel units, dtype per coords_kind
+ *   origin      (B,3) float32 metres            voxel_size  float (python float in the reference)
+ *   feats_nhwc  (V,B,H,W,C) float32             KRcam       (V,B,4,4) float32 world->pixel
+ *   out         (N,C+1) float32: view-mean features | normalised mean depth   (written for every row;
+ *               rows whose batch index is outside [0,B) are zero, as in the reference)
+ *   count       (N,) float32: number of views that see the voxel (bit-exact contract)
+ * workspace: d3m_back_project_fwd_workspace(N,B,V,C) bytes, 256-byte aligned.
+ * ------------------------------------------------------------------------------------------- */
+size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C);
+int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                         float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
+                         const float* KRcam, float* out, float* count, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * back_project backward w.r.t. feats  (replaces autograd through back_project.py:55-73:
+ * div backward, mask, grid_sampler_2d_backward).  Deterministic: samples are binned per texel with
+ * integer atomics only, each bin is ordered by voxel index, and every texel is accumulated by one
+ * lane group in a fixed order -- no floating-point atomics anywhere.
+ *   grad_out         (N,C+1) float32 (the depth column carries no gradient to feats)
+ *   grad_feats_nhwc  (V,B,H,W,C) float32, fully overwritten
+ * ------------------------------------------------------------------------------------------- */
+size_t d3m_back_project_bwd_workspace(int64_t N, int B, int V, int C, int H, int W);
+int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                         float voxel_size, int V, int C, int H, int W, const float* KRcam,
+                         const float* grad_out, float* grad_feats_nhwc, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * TSDF fusion  (replaces TSDFVolume, tsdf_volume.py:10-307, and TSDFVolumeTorch :485-574)
+ * The handle owns three (X,Y,Z) C-order float32 volumes on `device` (tsdf=1, weight=0, color=0:
+ * tsdf_volume.py:50-53), a pinned staging ring for host frames and the frame workspace.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct d3m_tsdf d3m_tsdf;
+
+/* integrate() arithmetic flavours */
+enum {
+  D3M_TSDF_KERNEL_SEMANTICS = 0, /* the reference CUDA kernel :68-126: roundf, cam_z<0 rejects, depth==0 rejects,
+                                    R^T(p-t) from cam_pose, nvcc FMA contraction of that source */
+  D3M_TSDF_TORCH_SEMANTICS = 1,  /* TSDFVolumeTorch :437-482: half-to-even, cam_z>0, depth>0, `pose` argument
+                                    is the fp32 world->camera matrix inverse(cam_pose), no contraction */
+  D3M_TSDF_WITH_COLOR = 2        /* flag (OR-ed): also run the colour average of :130-141, which the
+                                    reference kernel never reaches (:129); default keeps colour == 0 */
+};
+
+int d3m_tsdf_create(int dim_x, int dim_y, int dim_z, const float* origin3_host, float voxel_size,
+                    float trunc_margin, int device, d3m_tsdf** out_handle);
+int d3m_tsdf_destroy(d3m_tsdf* h);
+int d3m_tsdf_reset(d3m_tsdf* h, void* stream);
+
+/* One frame from HOST memory -- the shape of TSDFVolume.integrate (:210-256): depth (H,W) float32
+ * metres, optional colour (H,W) float32 already folded as b*65536+g*256+r (:223-227), intrinsics 3x3
+ * and pose 4x4 row-major float32.  Copies through the pinned ring, then runs the frame kernels. */
+int d3m_tsdf_integrate_host(d3m_tsdf* h, const float* depth_host, const float* color_host, int H, int W,
+                            const float* intr9_host, const float* pose16_host, float obs_weight,
+                            int flags, void* stream);
+
+/* n_frames frames already resident on the device, integrated in order inside ONE launch (each voxel
+ * block keeps its tsdf/weight in registers across the frames that touch it).
+ *   depth (n_frames,H,W); color (n_frames,H,W) or NULL; intr9_host (n_frames,9) or (1,9) when
+ *   intr_per_frame == 0; pose16_host (n_frames,16); obs_weight_host (n_frames) or NULL (= 1). */
+int d3m_tsdf_integrate_device(d3m_tsdf* h, const float* depth, const float* color, int n_frames, int H,
+                              int W, const float* intr9_host, int intr_per_frame,
+                              const float* pose16_host, const float* obs_weight_host, int flags,
+                              void* stream);
+
+/* device pointers of the volumes (valid until destroy) and a blocking copy to host (get_volume, :302-307) */
+int d3m_tsdf_volumes(d3m_tsdf* h, float** tsdf, float** weight, float** color);
+int d3m_tsdf_download(d3m_tsdf* h, float* tsdf_host, float* weight_host, float* color_host, void* stream);
+/* voxels whose weight changed in the last integrate call is not tracked; this returns the number of
+ * tile launches of the last call (diagnostics for bench.py's gpu_launches) */
+int d3m_tsdf_last_launches(d3m_tsdf* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* D3M_H_ */

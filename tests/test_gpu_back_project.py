@@ -1,0 +1,166 @@
+"""GPU parity tests of back_project (forward + deterministic backward) through the public drop-in API,
+i.e. through the C ABI of libd3m.so.  Checker = the C oracle (bit-exact pinned to the reference) plus the
+committed reference outputs in tests/golden/.
+
+Bars (BASELINE.json north_star): bit-exact for count / count>1 masks / valid-voxel sets; 1e-5 relative
+(atol 1e-6*max(1,rms)) for features, depth channel and gradients.  Features are additionally asserted
+bit-identical to the oracle because the kernel follows the same rounding sequence."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import cases
+from deep3dmap_b200 import synth
+
+from util import assert_close, assert_depth_channel_close, bp_inputs, check_bp_against_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def run_cuda(inp, grad=True, coords_dtype=None):
+    from deep3dmap_b200 import back_project
+    dev = torch.device("cuda:0")
+    coords = torch.from_numpy(inp["coords"])
+    if coords_dtype is not None:
+        coords = coords.to(coords_dtype)
+    feats = torch.from_numpy(inp["feats"]).to(dev).requires_grad_(grad)
+    vol, cnt = back_project(coords.to(dev), torch.from_numpy(inp["origin"]).to(dev), inp["voxel_size"], feats,
+                            torch.from_numpy(inp["KRcam"]).to(dev))
+    g = None
+    if grad:
+        vol.backward(torch.from_numpy(inp["grad_out"]).to(dev))
+        g = feats.grad.cpu().numpy()
+    torch.cuda.synchronize()
+    return vol.detach().cpu().numpy(), cnt.cpu().numpy(), g
+
+
+def check_vs_oracle(name, inp, vol, cnt, g):
+    C = inp["feats"].shape[2]
+    o_vol, o_cnt = oracle.back_project_fwd(inp["coords"], inp["origin"], inp["voxel_size"], inp["feats"], inp["KRcam"])
+    np.testing.assert_array_equal(cnt, o_cnt, err_msg=name + ": count")
+    np.testing.assert_array_equal(vol[:, :C], o_vol[:, :C], err_msg=name + ": features must be bit-exact vs oracle")
+    assert_depth_channel_close(vol[:, C], o_vol[:, C], name + ": depth channel")
+    if g is not None:
+        o_g = oracle.back_project_bwd(inp["coords"], inp["origin"], inp["voxel_size"], inp["feats"].shape, inp["KRcam"],
+                                      inp["grad_out"])
+        assert_close(g, o_g, name + ": grad_feats")
+
+
+@pytest.mark.parametrize("name", list(cases.BP_CASES))
+def test_matches_oracle_and_reference_golden(name):
+    inp, gold = bp_inputs(name)
+    vol, cnt, g = run_cuda(inp)
+    check_vs_oracle(name, inp, vol, cnt, g)
+    check_bp_against_golden(name, vol, cnt, g, gold, exact=False)
+
+
+@pytest.mark.parametrize("level", [0, 1, 2])
+def test_dense_levels_full_size(level):
+    """BASELINE config 1 shapes (dense 24^3 / 48^3 / 96^3, 9 views) against the oracle."""
+    inp = cases.bp_level(level)
+    vol, cnt, g = run_cuda(inp)
+    check_vs_oracle("dense L%d" % level, inp, vol, cnt, g)
+    S = {0: 53578, 1: 437635, 2: 3535706}[level]  # SURVEY.md §8d, measured with the reference
+    assert int(cnt.sum()) == S
+
+
+def test_backward_is_deterministic_bitwise():
+    inp = cases.bp_level(1, 30000, np.int64)
+    _, _, g1 = run_cuda(inp)
+    for _ in range(3):
+        _, _, g2 = run_cuda(inp)
+        np.testing.assert_array_equal(g1, g2)
+
+
+def test_many_views_chunked_and_generic_channels():
+    """V > 16 exercises the view-chunk loop; C = 7 the scalar-channel path; int32 coords the extension dtype."""
+    rng = np.random.default_rng(5)
+    V, B, C, H, W, N = 21, 2, 7, 10, 14, 900
+    R, c = synth.fragment_cameras(V)
+    K = np.array([[11.0, 0, 6.5], [0, 11.0, 4.5], [0, 0, 1]])
+    KR = np.stack([synth.krcam_from(R, c + np.array([0.0, 0.3 * b, 0.0]), K) for b in range(B)], 1)
+    coords = np.concatenate([rng.integers(0, B, (N, 1)), rng.integers(0, 96, (N, 3))], 1).astype(np.int32)
+    inp = dict(coords=coords, origin=np.zeros((B, 3), np.float32), voxel_size=0.04,
+               feats=rng.standard_normal((V, B, C, H, W), dtype=np.float32), KRcam=KR.astype(np.float32),
+               grad_out=rng.standard_normal((N, C + 1), dtype=np.float32))
+    vol, cnt, g = run_cuda(inp)
+    assert cnt.max() > 16
+    check_vs_oracle("V21 C7", inp, vol, cnt, g)
+
+
+@pytest.mark.parametrize("C", [8, 12, 16, 20, 32, 64, 96, 128])
+def test_other_channel_counts(C):
+    rng = np.random.default_rng(C)
+    inp = cases.bp_level(2, 3000, np.float32)
+    V, B, _, H, W = inp["feats"].shape
+    inp["feats"] = rng.standard_normal((V, B, C, H, W), dtype=np.float32)
+    inp["grad_out"] = rng.standard_normal((3000, C + 1), dtype=np.float32)
+    vol, cnt, g = run_cuda(inp)
+    check_vs_oracle("C=%d" % C, inp, vol, cnt, g)
+
+
+def test_empty_and_single_voxel():
+    inp = cases.bp_level(2, 1, np.float32)
+    vol, cnt, g = run_cuda(inp)
+    check_vs_oracle("N=1", inp, vol, cnt, g)
+    inp["coords"] = inp["coords"][:0]
+    inp["grad_out"] = inp["grad_out"][:0]
+    vol, cnt, g = run_cuda(inp)
+    assert vol.shape == (0, 25) and cnt.shape == (0,) and (g == 0).all()
+
+
+def test_channels_last_input_is_zero_copy_and_equal():
+    from deep3dmap_b200 import back_project
+    inp = cases.bp_level(1, 5000, np.int64)
+    dev = torch.device("cuda:0")
+    f_nchw = torch.from_numpy(inp["feats"]).to(dev)
+    f_cl = f_nchw.permute(0, 1, 3, 4, 2).contiguous().permute(0, 1, 4, 2, 3)  # same values, channels-last storage
+    args = (torch.from_numpy(inp["coords"]).to(dev), torch.from_numpy(inp["origin"]).to(dev), inp["voxel_size"])
+    KR = torch.from_numpy(inp["KRcam"]).to(dev)
+    v1, c1 = back_project(*args, f_nchw, KR)
+    v2, c2 = back_project(*args, f_cl, KR)
+    assert torch.equal(v1, v2) and torch.equal(c1, c2)
+
+
+def test_adjoint_identity_full_size():
+    """Size-independent property at the dense level-2 size (N = 884,736, 7.96 M samples):
+    <J feats, G> == <feats, J^T G> for the feature block (the op is linear in feats)."""
+    from deep3dmap_b200 import back_project
+    inp = cases.bp_level(2)
+    dev = torch.device("cuda:0")
+    C = 24
+    feats = torch.from_numpy(inp["feats"]).to(dev).requires_grad_(True)
+    vol, cnt = back_project(torch.from_numpy(inp["coords"]).to(dev), torch.from_numpy(inp["origin"]).to(dev),
+                            inp["voxel_size"], feats, torch.from_numpy(inp["KRcam"]).to(dev))
+    G = torch.from_numpy(inp["grad_out"]).to(dev)
+    vol.backward(G)
+    lhs = (vol[:, :C].double() * G[:, :C].double()).sum().item()
+    rhs = (feats.detach().double() * feats.grad.double()).sum().item()
+    assert abs(lhs - rhs) <= 1e-6 * max(abs(lhs), abs(rhs), 1.0), (lhs, rhs)
+    # linearity: doubling feats doubles the features, leaves count and the depth channel unchanged
+    vol2, cnt2 = back_project(torch.from_numpy(inp["coords"]).to(dev), torch.from_numpy(inp["origin"]).to(dev),
+                              inp["voxel_size"], feats.detach() * 2, torch.from_numpy(inp["KRcam"]).to(dev))
+    assert torch.equal(vol2[:, :C], vol[:, :C].detach() * 2) and torch.equal(cnt2, cnt)
+    assert torch.equal(vol2[:, C], vol[:, C].detach())
+
+
+def test_batched_fragments_equal_individual_calls():
+    """Fragment-parallel contract (config 4): one call with B fragments == B single-fragment calls."""
+    from deep3dmap_b200 import back_project
+    dev = torch.device("cuda:0")
+    B = 4
+    inp = synth.fragment_level_inputs(1, batch=B, coords_dtype=np.float32)
+    rng = np.random.default_rng(3)
+    keep = np.sort(rng.choice(inp["coords"].shape[0], 20000, replace=False))
+    coords = inp["coords"][keep]
+    t = lambda a: torch.from_numpy(a).to(dev)
+    vol, cnt = back_project(t(coords), t(inp["origin"]), 0.04, t(inp["feats"]), t(inp["KRcam"]))
+    for b in range(B):
+        m = coords[:, 0] == b
+        cb = coords[m].copy()
+        cb[:, 0] = 0
+        vb, cntb = back_project(t(cb), t(inp["origin"][b:b + 1]), 0.04, t(inp["feats"][:, b:b + 1].copy()),
+                                t(inp["KRcam"][:, b:b + 1].copy()))
+        mm = torch.from_numpy(m).to(dev)
+        assert torch.equal(vol[mm], vb) and torch.equal(cnt[mm], cntb)

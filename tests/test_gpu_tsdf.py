@@ -1,0 +1,179 @@
+"""GPU parity tests of TSDF fusion through the drop-in classes (C ABI of libd3m.so).
+
+Checkers: the C oracle (same rounding sequence -> weights AND tsdf bit-exact), the reference's own CUDA
+kernel compiled verbatim into oracle/_ref/libref_tsdf.so (bit-exact, when that file travelled with the
+snapshot), and the reference CPU outputs in tests/golden/."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import cases
+
+from util import load_golden, tsdf_decision_margin
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libref_tsdf.so")
+
+
+def run_ours(c, batch=False, color=False):
+    from deep3dmap_b200 import TSDFVolume
+    v = TSDFVolume(c["vol_bnds"].copy(), c["voxel_size"], margin=c["margin"], integrate_color=color)
+    if batch:
+        depths = np.stack([d for d, _ in c["frames"]])
+        poses = np.stack([p for _, p in c["frames"]])
+        v.integrate_batch(depths, c["K"], poses, c["obs_weights"], np.stack(c["colors"]) if color else None)
+    else:
+        for i, ((depth, pose), w) in enumerate(zip(c["frames"], c["obs_weights"])):
+            v.integrate(c["colors"][i] if color else None, depth, c["K"], pose, w)
+    t, col, w = v.get_volume()
+    return v, t.copy(), col.copy(), w.copy()
+
+
+def run_oracle(c, color=False):
+    o = oracle.TSDFVolumeOracle(c["vol_bnds"].copy(), c["voxel_size"], margin=c["margin"], with_color=color)
+    for i, ((depth, pose), w) in enumerate(zip(c["frames"], c["obs_weights"])):
+        o.integrate(c["colors"][i] if color else None, depth, c["K"], pose, w)
+    return o.get_volume()
+
+
+@pytest.mark.parametrize("name", cases.TSDF_CASES)
+@pytest.mark.parametrize("batch", [False, True])
+def test_bit_exact_vs_oracle(name, batch):
+    c = cases.tsdf_case(name)
+    v, t, col, w = run_ours(c, batch=batch)
+    ot, ocol, ow = run_oracle(c)
+    np.testing.assert_array_equal(w, ow)
+    np.testing.assert_array_equal(t, ot)
+    assert (col == 0).all()  # reference GPU kernel never integrates colour (tsdf_volume.py:129)
+    assert v.gpu_launches > 0
+
+
+@pytest.mark.parametrize("name", cases.TSDF_CASES)
+def test_vs_reference_cpu_golden(name):
+    c = cases.tsdf_case(name)
+    g = load_golden("tsdf_" + name)
+    v, t, col, w = run_ours(c)
+    np.testing.assert_array_equal(v._vol_dim, g["dims"])
+    flips = np.flatnonzero(w.reshape(-1) != g["np_weight"].reshape(-1))
+    assert flips.size <= max(2, int(2e-5 * g["np_tsdf_idx"].size))
+    for i in flips:
+        assert tsdf_decision_margin(c, g["dims"], g["origin"], i) < 1e-4
+    same = np.setdiff1d(g["np_tsdf_idx"], flips)
+    ref_val = g["np_tsdf_val"][np.isin(g["np_tsdf_idx"], same)]
+    np.testing.assert_allclose(t.reshape(-1)[same], ref_val, rtol=1e-5, atol=5e-5)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SO), reason="oracle/_ref/libref_tsdf.so not built (reference tree absent)")
+@pytest.mark.parametrize("name", cases.TSDF_CASES)
+def test_bit_exact_vs_verbatim_reference_cuda_kernel(name):
+    """The reference's own CUDA string (tsdf_volume.py:68-142), compiled by oracle/build_ref.py, run on this GPU."""
+    c = cases.tsdf_case(name)
+    _, t, col, w = run_ours(c)
+    L = ctypes.CDLL(REF_SO)
+    vp, i32, f32 = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    L.ref_tsdf_integrate.argtypes = [vp, vp, vp, i32, i32, i32, vp, vp, vp, f32, i32, i32, f32, f32, vp, vp, vp]
+    L.ref_tsdf_integrate.restype = i32
+    o = oracle.TSDFVolumeOracle(c["vol_bnds"].copy(), c["voxel_size"], margin=c["margin"])
+    dims = [int(d) for d in o._vol_dim]
+    dev = torch.device("cuda:0")
+    rt = torch.ones(dims, device=dev)
+    rw = torch.zeros(dims, device=dev)
+    rc_ = torch.zeros(dims, device=dev)
+    for (depth, pose), wgt in zip(c["frames"], c["obs_weights"]):
+        d = torch.from_numpy(depth).to(dev)
+        K = np.ascontiguousarray(c["K"].reshape(-1).astype(np.float32))
+        T = np.ascontiguousarray(pose.reshape(-1).astype(np.float32))
+        torch.cuda.synchronize()
+        rc = L.ref_tsdf_integrate(rt.data_ptr(), rw.data_ptr(), rc_.data_ptr(), dims[0], dims[1], dims[2],
+                                  o._vol_origin.ctypes.data, K.ctypes.data, T.ctypes.data,
+                                  np.float32(c["voxel_size"]), depth.shape[0], depth.shape[1],
+                                  np.float32(c["margin"] * c["voxel_size"]), np.float32(wgt), d.data_ptr(),
+                                  d.data_ptr(), None)
+        assert rc == 0
+    np.testing.assert_array_equal(w, rw.cpu().numpy())
+    np.testing.assert_array_equal(t, rt.cpu().numpy())
+
+
+def test_colour_opt_in_matches_oracle():
+    c = cases.tsdf_case("orbit_weighted")
+    for batch in (False, True):
+        _, t, col, w = run_ours(c, batch=batch, color=True)
+        ot, ocol, ow = run_oracle(c, color=True)
+        np.testing.assert_array_equal(w, ow)
+        np.testing.assert_array_equal(t, ot)
+        np.testing.assert_array_equal(col, ocol)
+        assert col.max() > 0
+
+
+@pytest.mark.parametrize("name", cases.TSDF_CASES)
+def test_torch_semantics_bit_exact_vs_reference_golden(name):
+    """TSDFVolumeTorch drop-in vs the reference TSDFVolumeTorch outputs (fixtures): weights and tsdf bit-exact."""
+    from deep3dmap_b200 import TSDFVolumeTorch
+    c = cases.tsdf_case(name)
+    g = load_golden("tsdf_" + name)
+    for batch in (False, True):
+        v = TSDFVolumeTorch(torch.tensor(g["dims"]), torch.from_numpy(g["origin"]), c["voxel_size"], margin=c["margin"])
+        if batch:
+            v.integrate_batch(torch.from_numpy(np.stack([d for d, _ in c["frames"]])), torch.from_numpy(c["K"]),
+                              [torch.from_numpy(p) for _, p in c["frames"]], c["obs_weights"])
+        else:
+            for (depth, pose), w in zip(c["frames"], c["obs_weights"]):
+                v.integrate(torch.from_numpy(depth), torch.from_numpy(c["K"]), torch.from_numpy(pose), w)
+        t, w = [x.numpy() for x in v.get_volume()]
+        np.testing.assert_array_equal(w, g["torch_weight"])
+        np.testing.assert_array_equal(t.reshape(-1)[g["torch_tsdf_idx"]], g["torch_tsdf_val"])
+        assert (t[w == 0] == 1).all()
+
+
+def test_large_volume_batch_equals_sequential():
+    """BASELINE config 3 scale property: 512^3 @ 4 cm, 480x640 frames -- one batched launch over 12 frames must
+    equal 12 per-frame integrate() calls bit for bit, and frames far outside the volume must change nothing."""
+    from deep3dmap_b200 import TSDFVolume, synth
+    bnds = np.array([[0.0, 20.48]] * 3)
+    K = synth.tsdf_intrinsics()
+    frames = list(range(0, 36, 3))
+    depths = np.stack([synth.tsdf_depth(f) for f in frames])
+    poses = np.stack([synth.tsdf_pose(f) for f in frames])
+    a = TSDFVolume(bnds.copy(), 0.04, margin=3)
+    assert tuple(a._vol_dim) == (512, 512, 512)
+    for d, p in zip(depths, poses):
+        a.integrate(None, d, K, p, 1.0)
+    b = TSDFVolume(bnds.copy(), 0.04, margin=3)
+    b.integrate_batch(depths, K, poses)
+    ta, _, wa = a.get_volume()
+    tb, _, wb = b.get_volume()
+    np.testing.assert_array_equal(wa, wb)
+    np.testing.assert_array_equal(ta, tb)
+    n_upd = int((wa > 0).sum())
+    assert n_upd > 100000 and wa.max() >= 2
+    far = poses[0].copy()
+    far[:3, 3] += 100.0
+    b.integrate(None, depths[0], K, far, 1.0)
+    _, _, wb2 = b.get_volume()
+    np.testing.assert_array_equal(wb, wb2)
+    del a, b
+
+
+def test_oracle_subvolume_of_large_scene():
+    """Same 512^3 scene, checked against the oracle on a 96^3 sub-box around the camera orbit."""
+    from deep3dmap_b200 import TSDFVolume, synth
+    K = synth.tsdf_intrinsics()
+    lo = np.array([10.24 + 0.64, 10.24 - 1.28, 0.0])
+    bnds = np.stack([lo, lo + 96 * 0.04], 1)
+    frames = [0, 1, 2, 5, 9]
+    v = TSDFVolume(bnds.copy(), 0.04, margin=3)
+    o = oracle.TSDFVolumeOracle(bnds.copy(), 0.04, margin=3)
+    for f in frames:
+        d, p = synth.tsdf_depth(f), synth.tsdf_pose(f)
+        v.integrate(None, d, K, p, 1.0)
+        o.integrate(None, d, K, p, 1.0)
+    t, _, w = v.get_volume()
+    ot, _, ow = o.get_volume()
+    np.testing.assert_array_equal(w, ow)
+    np.testing.assert_array_equal(t, ot)
+    assert (ow > 0).sum() > 50000
