@@ -1,0 +1,522 @@
+#!/usr/bin/env python
+"""bench.py -- headline measurement of the NeuralRecon lifting hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one pass of the hot path over one synthetic ScanNet-shaped fragment (BASELINE.json configs[1]):
+back_project forward + backward at the 3 coarse-to-fine levels (level 0 dense 24^3, levels 1-2 sparse after
+the occupancy pruning / TRAIN_NUM_SAMPLE cap of the reference, int64 coords), 9 views of 480x640 -> 24/40/80
+channel maps.  metric = voxel-view samples/s, samples = sum_levels N_level * 9.  With N GPUs every rank owns its
+own fragment (fragment-parallel, BASELINE configs[3]; no data-path collective) -> weak scaling.
+The same JSON line also carries the TSDF leg (BASELINE configs[2]: 640x480 frames into a 512^3 volume @ 4 cm).
+
+Exactly ONE JSON line is printed on stdout (rank 0); progress goes to stderr.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from deep3dmap_b200 import synth  # noqa: E402
+
+WORKLOAD = "neuralrecon_fragment_c2f_sparse_3level_fwd_bwd"
+METRIC = "voxel-view samples/s (back_project fwd+bwd)"
+N_TSDF_FRAMES = 300
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------
+# workload construction (host side, numpy)
+# --------------------------------------------------------------------------------------------------
+def build_fragment_levels(count_fn, frag_seed=0):
+    """The 3 back_project calls of one fragment.  `count_fn(level_inputs) -> count (N,)` supplies the view
+    counts that drive the synthetic occupancy pruning (neucon_network.py:180-196)."""
+    off = (3.84 * (frag_seed % 8), 3.84 * (frag_seed // 8), 0.0)
+    levels = []
+    coords = None
+    for lv in range(synth.N_LAYER):
+        inp = synth.fragment_level_inputs(lv, batch=1, coords=coords, frag_offsets=[off])
+        inp["feats"] = synth.feats_for(lv, seed_offset=100 * frag_seed)
+        if lv == 0:
+            inp["coords"] = synth.dense_coords(synth.LEVELS[0]["interval"], 0, np.float32)
+        C = synth.LEVELS[lv]["C"]
+        inp["grad_out"] = synth.grad_out_for(inp["coords"].shape[0], C, seed=99 + lv)
+        levels.append(inp)
+        if lv + 1 < synth.N_LAYER:
+            cnt = count_fn(inp)
+            keep = synth.synthetic_occupancy(inp["coords"], cnt, lv)
+            pre = inp["coords"][keep].astype(np.int64)
+            coords = synth.upsample_coords(pre, synth.LEVELS[lv + 1]["interval"])
+    return levels
+
+
+def algorithmic_bytes(level_inp, S):
+    """A_fwd = N(cb+4(C+1)+4) + 16 C S + 64 V B ; A_bwd = N(cb+4(C+1)+4) + 16 C S + 4 V B C H W."""
+    V, B, C, H, W = level_inp["feats"].shape
+    N = level_inp["coords"].shape[0]
+    cb = level_inp["coords"].dtype.itemsize * 4
+    a_fwd = N * (cb + 4 * (C + 1) + 4) + 16 * C * S + 64 * V * B
+    a_bwd = N * (cb + 4 * (C + 1) + 4) + 16 * C * S + 4 * V * B * C * H * W
+    return a_fwd, a_bwd
+
+
+# --------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# --------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port on the host cores
+# --------------------------------------------------------------------------------------------------
+def oracle_step(levels, oracle):
+    for inp in levels:
+        oracle.back_project_fwd(inp["coords"], inp["origin"], inp["voxel_size"], inp["feats"], inp["KRcam"])
+        oracle.back_project_bwd(inp["coords"], inp["origin"], inp["voxel_size"], inp["feats"].shape, inp["KRcam"],
+                                inp["grad_out"])
+
+
+def oracle_count_fn(oracle):
+    def f(inp):
+        return oracle.back_project_fwd(inp["coords"], inp["origin"], inp["voxel_size"], inp["feats"], inp["KRcam"])[1]
+    return f
+
+
+def cpu_baseline_bp(levels, steps, warmup):
+    import oracle
+    for _ in range(max(1, warmup)):
+        oracle_step(levels, oracle)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        oracle_step(levels, oracle)
+        ts.append(time.perf_counter() - t0)
+    samples = sum(l["coords"].shape[0] for l in levels) * synth.N_VIEWS
+    return samples / (sum(ts) / len(ts)), sum(ts) / len(ts), oracle.num_threads()
+
+
+def cpu_baseline_tsdf(n_frames=3):
+    import oracle
+    bnds = np.array([[0.0, 20.48]] * 3)
+    v = oracle.TSDFVolumeOracle(bnds, 0.04, margin=3)
+    K = synth.tsdf_intrinsics()
+    v.integrate(None, synth.tsdf_depth(0), K, synth.tsdf_pose(0), 1.0)  # warm-up (page faults of the 3 volumes)
+    t = 0.0
+    for f in range(1, 1 + n_frames):
+        d, p = synth.tsdf_depth(f), synth.tsdf_pose(f)
+        t0 = time.perf_counter()
+        v.integrate(None, d, K, p, 1.0)
+        t += time.perf_counter() - t0
+    return n_frames / t, oracle.num_threads()
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import oracle
+    levels = build_fragment_levels(oracle_count_fn(oracle))
+    steps = max(1, min(args.steps, 10))
+    v, sec, cores = cpu_baseline_bp(levels, steps, min(args.warmup, 2))
+    tsdf_fps, _ = cpu_baseline_tsdf(3)
+    samples = sum(l["coords"].shape[0] for l in levels) * synth.N_VIEWS
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "levels_N": [int(l["coords"].shape[0]) for l in levels], "views": synth.N_VIEWS,
+                   "samples_per_step": int(samples)},
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "%d full steps of the same 3-level fragment on the host cores (OpenMP C port of the "
+                                   "reference algorithm, oracle/d3m_oracle.c)" % steps},
+        "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "tsdf": {"frames_per_s": tsdf_fps, "unit": "frames/s", "volume": "512^3 @ 4 cm", "sample": "3 frames, C port"},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from deep3dmap_b200 import _lib, back_project, TSDFVolume
+    from deep3dmap_b200 import voxel
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback in this build)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak_gbs, peak_src = measured_peaks()
+
+    def t(a):
+        return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+    def cuda_count(inp):
+        _, cnt = back_project(t(inp["coords"]), t(inp["origin"]), inp["voxel_size"], t(inp["feats"]), t(inp["KRcam"]))
+        return cnt.cpu().numpy()
+
+    levels = build_fragment_levels(cuda_count, frag_seed=rank)
+    samples = sum(l["coords"].shape[0] for l in levels) * synth.N_VIEWS
+    log("[rank %d] levels N = %s, samples/step = %d" % (rank, [l["coords"].shape[0] for l in levels], samples))
+
+    # ---- device-resident inputs -------------------------------------------------------------------
+    dl = []
+    for inp in levels:
+        dl.append(dict(coords=t(inp["coords"]), origin=t(inp["origin"]), vs=inp["voxel_size"],
+                       feats=t(inp["feats"]).requires_grad_(True), KR=t(inp["KRcam"]), go=t(inp["grad_out"])))
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_resident():
+        outs = []
+        for d in dl:
+            d["feats"].grad = None
+            vol, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+            vol.backward(d["go"])
+            outs.append((vol, cnt))
+        return outs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    barrier()
+    if args.profile_step:
+        # target for `ncu`: nothing but K flushed steps of the hot path (no JSON; numbers under a profiler are not bench values)
+        for _ in range(args.steps):
+            flush_buf.fill_(1)
+            step_resident()
+        torch.cuda.synchronize()
+        if args.profile_step == "tsdf":
+            bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=True)
+        return
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    # ---- timed region 1: inputs resident in HBM, L2 flushed between steps ---------------------------
+    launches0 = _lib.kernel_launches()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for a, b in ev:
+        flush_buf.fill_(1)
+        a.record()
+        step_resident()
+        b.record()
+    barrier()
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    # host-side issue cost of one step (python + ctypes + launches), GPU idle at start
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step_resident()
+    host_ms = (time.perf_counter() - t0) / 5 * 1e3
+    torch.cuda.synchronize()
+    launches = _lib.kernel_launches() - launches0
+    ms_step = float(np.mean(ms_steps))
+
+    # ---- timed region 2 (e2e): host buffers in, host buffers out, through the public API ------------
+    pin = []
+    h2d = d2h = 0
+    for inp in levels:
+        hp = {k: torch.from_numpy(np.ascontiguousarray(inp[k])).pin_memory() for k in ("coords", "origin", "feats", "KRcam", "grad_out")}
+        V, B, C, H, W = inp["feats"].shape
+        N = inp["coords"].shape[0]
+        hp["o_vol"] = torch.empty((N, C + 1), dtype=torch.float32).pin_memory()
+        hp["o_cnt"] = torch.empty((N,), dtype=torch.float32).pin_memory()
+        hp["o_grad"] = torch.empty((V, B, C, H, W), dtype=torch.float32).pin_memory()
+        hp["vs"] = inp["voxel_size"]
+        h2d += sum(hp[k].numel() * hp[k].element_size() for k in ("coords", "origin", "feats", "KRcam", "grad_out"))
+        d2h += sum(hp[k].numel() * hp[k].element_size() for k in ("o_vol", "o_cnt", "o_grad"))
+        pin.append(hp)
+
+    def step_e2e():
+        for hp in pin:
+            c = hp["coords"].to(dev, non_blocking=True)
+            o = hp["origin"].to(dev, non_blocking=True)
+            f = hp["feats"].to(dev, non_blocking=True).requires_grad_(True)
+            k = hp["KRcam"].to(dev, non_blocking=True)
+            g = hp["grad_out"].to(dev, non_blocking=True)
+            vol, cnt = back_project(c, o, hp["vs"], f, k)
+            vol.backward(g)
+            hp["o_vol"].copy_(vol.detach(), non_blocking=True)
+            hp["o_cnt"].copy_(cnt, non_blocking=True)
+            hp["o_grad"].copy_(f.grad, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(3):
+        step_e2e()
+    e2e_steps = max(3, args.steps // 2)
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(e2e_steps)]
+    for a, b in ev2:
+        flush_buf.fill_(1)
+        a.record()
+        step_e2e()
+        b.record()
+    barrier()
+    ms_e2e = float(np.mean([a.elapsed_time(b) for a, b in ev2]))
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- roofline pass: per-kernel CUDA events inside the library, same steps, same L2 flush ---------
+    S_levels = []
+    prof = {}
+    if rank == 0:
+        for d, inp in zip(dl, levels):
+            with torch.no_grad():
+                _, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+            S_levels.append(int(cnt.sum().item()))
+        per_level = []
+        for li, d in enumerate(dl):
+            acc = {}
+            for _ in range(args.steps):
+                flush_buf.fill_(1)
+                torch.cuda.synchronize()
+                _lib.profile_begin()
+                d["feats"].grad = None
+                vol, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+                vol.backward(d["go"])
+                for k, v in _lib.profile_end().items():
+                    e = acc.setdefault(k, {"n": 0, "ms": 0.0})
+                    e["n"] += v["n"]; e["ms"] += v["ms"]
+            per_level.append(acc)
+        prof = per_level
+
+    # ---- TSDF leg (rank 0 only; replicas only across ranks) -------------------------------------------
+    tsdf = None
+    if rank == 0:
+        tsdf = bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf)
+
+    # ---- aggregate ---------------------------------------------------------------------------------------
+    if world > 1:
+        tt = torch.tensor([ms_step, ms_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_step, ms_e2e = float(tt[0]), float(tt[1])
+        tot = torch.tensor([float(samples)], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+        total_samples = float(tot[0])
+    else:
+        total_samples = float(samples)
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = total_samples / (ms_step * 1e-3)
+    e2e_value = total_samples / (ms_e2e * 1e-3)
+    # dominant kernel over the whole step and its roofline
+    tot_ms = {}
+    for acc in prof:
+        for k, v in acc.items():
+            tot_ms[k] = tot_ms.get(k, 0.0) + v["ms"]
+    kern_total = sum(tot_ms.values())
+    dom = max(tot_ms, key=tot_ms.get)
+    # dominant (kernel, level) pair: algorithmic bytes are per level
+    best = None
+    for li, acc in enumerate(prof):
+        if dom in acc:
+            a_fwd, a_bwd = algorithmic_bytes(levels[li], S_levels[li])
+            ms = acc[dom]["ms"] / max(1, acc[dom]["n"])
+            if best is None or acc[dom]["ms"] > best[0]:
+                best = (acc[dom]["ms"], li, ms, a_fwd, a_bwd)
+    _, li, ms_k, a_fwd, a_bwd = best
+    V, B, C, H, W = levels[li]["feats"].shape
+    if dom == "bp_fwd":
+        alg = a_fwd
+    elif dom == "bp_bwd_gather":
+        alg = 16 * C * S_levels[li] + 4 * V * B * C * H * W + 16 * S_levels[li]
+    else:
+        alg = a_bwd
+    achieved = alg / (ms_k * 1e-3) / 1e9
+    a_path = sum(sum(algorithmic_bytes(l, s)) for l, s in zip(levels, S_levels))
+    path_gbs = a_path / (ms_step * 1e-3) / 1e9
+    cpu_v, cpu_sec, cores = cpu_baseline_bp(levels, 5, 1)
+    line = {
+        "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "levels_N": [int(l["coords"].shape[0]) for l in levels],
+                   "levels_valid_samples": S_levels, "views": synth.N_VIEWS, "channels": [80, 40, 24],
+                   "coords_dtype": ["float32", "int64", "int64"], "samples_per_step": int(samples),
+                   "fragments_per_gpu": 1, "parallelism": "fragment-parallel x%d (no data-path collective)" % world,
+                   "l2": "256 MiB buffer written between timed steps (L2 flush); per-step CUDA events"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": ms_e2e, "what": "back_project() public API from pinned host tensors; volume, count and "
+                "grad_feats copied back to pinned host memory every step"},
+        "gpu_launches": int(launches), "host_issue_ms_per_step": host_ms,
+        "roofline": {"bound": "hbm", "kernel": dom, "level": li, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": int(alg), "ms_per_launch": ms_k,
+                     "kernel_share_of_step": tot_ms[dom] / kern_total,
+                     "note": "feature maps are L2-resident at fragment size (SURVEY §8d): bytes are algorithmic "
+                             "gather bytes, mostly served by L2"},
+        "path_roofline": {"algorithmic_bytes_per_step": int(a_path), "achieved": path_gbs, "frac": path_gbs / peak_gbs,
+                          "frac_of_nominal_8TBs": path_gbs / 8000.0},
+        "kernel_ms_per_step": {k: v / args.steps for k, v in sorted(tot_ms.items())},
+        "kernel_us_per_level": [{k: round(1e3 * v["ms"] / args.steps, 2) for k, v in sorted(acc.items())} for acc in prof],
+        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
+                         "sample": "5 full steps of the same fragment on the host (OpenMP C port of the reference "
+                                   "algorithm; %.1f ms/step)" % (cpu_sec * 1e3)},
+        "tsdf": tsdf,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=False):
+    """BASELINE configs[2]: 300 synthetic 640x480 depth frames into a 512^3 volume at 4 cm."""
+    F = N_TSDF_FRAMES
+    K = synth.tsdf_intrinsics()
+    depths = np.stack([synth.tsdf_depth(f) for f in range(F)])
+    poses = np.stack([synth.tsdf_pose(f) for f in range(F)])
+    bnds = np.array([[0.0, 20.48]] * 3)
+    vol = TSDFVolume(bnds.copy(), 0.04, margin=3)
+    d_dev = torch.from_numpy(depths).to(dev)
+    res = {"volume": "512^3 @ 4 cm", "frames": F, "image": "480x640", "unit": "frames/s"}
+    # (a) resident frames, one launch for all frames
+    vol.integrate_batch(d_dev, K, poses)
+    torch.cuda.synchronize()
+    if quick:
+        vol.reset()
+        vol.integrate_batch(d_dev, K, poses)
+        for f in range(8):
+            vol.integrate_batch(d_dev[f:f + 1], K, poses[f:f + 1])
+        torch.cuda.synchronize()
+        return None
+    ts = []
+    for _ in range(5):
+        vol.reset()
+        flush_buf.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); vol.integrate_batch(d_dev, K, poses); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    res["frames_per_s"] = F / (min(ts) * 1e-3)
+    res["ms_batch_300"] = min(ts)
+    t_w = torch.as_tensor(vol.device_volumes()[1], device=dev)
+    U = int((t_w > 0).sum().item())
+    alg = 16 * U + 4 * 480 * 640 * F
+    res["roofline"] = {"bound": "hbm", "kernel": "tsdf_integrate (batched)", "algorithmic_bytes": int(alg),
+                       "achieved": alg / (min(ts) * 1e-3) / 1e9, "peak": peak_gbs, "unit": "GB/s",
+                       "frac": alg / (min(ts) * 1e-3) / 1e9 / peak_gbs, "touched_voxels": U,
+                       "note": "projection-bound, not HBM-bound: 16 B per touched voxel + depth once (SURVEY §8d)"}
+    # (b) per-frame calls, frames resident
+    vol.reset()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for f in range(F):
+        vol.integrate_batch(d_dev[f:f + 1], K, poses[f:f + 1])
+    b.record(); torch.cuda.synchronize()
+    res["frames_per_s_per_call_resident"] = F / (a.elapsed_time(b) * 1e-3)
+    # (c) e2e: the reference call, numpy frame in host memory every call
+    vol.reset()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in range(F):
+        vol.integrate(None, depths[f], K, poses[f], 1.0)
+    torch.cuda.synchronize()
+    res["e2e_frames_per_s"] = F / (time.perf_counter() - t0)
+    res["e2e_h2d_bytes_per_frame"] = 480 * 640 * 4
+    # (d) data-gen composite: 3 volumes (4/8/16 cm) per frame, tools/data_gen/scannet.py:96-100
+    vols = [TSDFVolume(bnds.copy(), 0.04 * 2 ** l, margin=3) for l in range(3)]
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for f in range(F):
+        for v in vols:
+            v.integrate(None, depths[f], K, poses[f], 1.0)
+    torch.cuda.synchronize()
+    res["e2e_datagen_3level_fps"] = F / (time.perf_counter() - t0)
+    cpu_fps, cores = cpu_baseline_tsdf(3)
+    res["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                           "sample": "3 frames into the same 512^3 volume, OpenMP C port of the reference kernel"}
+    res["gpu_launches"] = int(vol.gpu_launches)
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--profile-step", default="", choices=["", "bp", "tsdf"],
+                    help="profiler target: run only the hot-path steps (and the TSDF launches with 'tsdf'), print nothing")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libd3m.so")
 # every symbol include/d3m.h declares
 SYMBOLS = (
     "d3m_version", "d3m_last_error", "d3m_device_count",
+    "d3m_kernel_launches", "d3m_profile_begin", "d3m_profile_end",
     "d3m_feats_nchw_to_nhwc", "d3m_feats_nhwc_to_nchw",
     "d3m_back_project_fwd_workspace", "d3m_back_project_fwd",
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
@@ -42,6 +43,10 @@ def lib():
     L.d3m_version.restype = i32
     L.d3m_last_error.restype = ctypes.c_char_p
     L.d3m_device_count.restype = i32
+    L.d3m_kernel_launches.restype = i64
+    L.d3m_profile_begin.restype = i32
+    L.d3m_profile_end.argtypes = [ctypes.c_char_p, sz]
+    L.d3m_profile_end.restype = i32
     for name in ("d3m_feats_nchw_to_nhwc", "d3m_feats_nhwc_to_nchw"):
         f = getattr(L, name)
         f.argtypes = [vp, vp, i64, i32, i32, i32, vp]
@@ -52,7 +57,7 @@ def lib():
     L.d3m_back_project_fwd.restype = i32
     L.d3m_back_project_bwd_workspace.argtypes = [i64, i32, i32, i32, i32, i32]
     L.d3m_back_project_bwd_workspace.restype = sz
-    L.d3m_back_project_bwd.argtypes = [vp, i32, i64, vp, i32, f32, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.d3m_back_project_bwd.argtypes = [vp, i32, i64, vp, i32, f32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, sz, vp]
     L.d3m_back_project_bwd.restype = i32
     L.d3m_tsdf_create.argtypes = [i32, i32, i32, vp, f32, f32, i32, ctypes.POINTER(vp)]
     L.d3m_tsdf_create.restype = i32
@@ -83,3 +88,19 @@ def check(rc, what):
 def require_device():
     if lib().d3m_device_count() <= 0:
         raise D3MError("deep3dmap_b200: no CUDA device visible -- this path has no CPU fallback")
+
+
+def kernel_launches():
+    return int(lib().d3m_kernel_launches())
+
+
+def profile_begin():
+    check(lib().d3m_profile_begin(), "d3m_profile_begin")
+
+
+def profile_end():
+    """-> {kernel name: {"n": launches, "ms": total device ms}} measured with CUDA events on the launching stream."""
+    import json
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().d3m_profile_end(buf, len(buf)), "d3m_profile_end")
+    return json.loads(buf.value.decode())

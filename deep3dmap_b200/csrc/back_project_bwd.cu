@@ -21,9 +21,8 @@
 namespace d3m {
 
 constexpr unsigned kFullB = 0xffffffffu;
-constexpr int kPrepThreads = 256;
 constexpr int kScanThreads = 256;
-constexpr int kScanItems = 16;
+constexpr int kScanItems = 8;
 constexpr int kScanChunk = kScanThreads * kScanItems;
 constexpr int kGatherWarps = 8;
 
@@ -36,141 +35,127 @@ struct BwdParams {
   int V, C, H, W;
   const float* KR;
   const float* grad_out;
+  const float* count;  // (N,) view counts from the forward pass, or the workspace copy computed by bp_bwd_count_kernel
   float* ghat;
   int* bin_cnt;
   int* bin_start;  // M+1
   int4* entries;
   float* grad_feats;
   int64_t M;  // V*B*H*W cells
-  int* chunk_sums;
-  unsigned int* counter;
+  unsigned long long* scan_state;  // nchunks words, zeroed together with bin_cnt
+  unsigned int* counter;           // scan ticket, zeroed together with bin_cnt
   int nchunks;
+  int grad_nchw;                   // 1: gather writes (V,B,C,H,W) directly
 };
 
-template <int KIND, bool FILL>
-__device__ __forceinline__ int project_all_views(const BwdParams& p, int64_t n, int* __restrict__ bin_cnt) {
+constexpr int kSampleThreads = 256;
+constexpr int kGhatPerThread = 4;
+
+// Only used when the caller does not hand over the forward pass's `count`: valid views per voxel.
+template <int KIND>
+__global__ void __launch_bounds__(kSampleThreads) bp_bwd_count_kernel(const BwdParams p, float* __restrict__ cnt_out) {
+  const int64_t n = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
+  if (n >= p.N) return;
   float cx, cy, cz;
   const int b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
-  if (b < 0) return 0;
+  int cnt = 0;
+  if (b >= 0) {
+    float gx, gy, gz;
+    const float* o = p.origin + 3 * b;
+    voxel_world(cx, cy, cz, p.vs, __ldg(o), __ldg(o + 1), __ldg(o + 2), gx, gy, gz);
+    const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
+    for (int v = 0; v < p.V; ++v) {
+      float4 r0, r1, r2;
+      load_krcam(p.KR, v, p.B, b, r0, r1, r2);
+      cnt += project(gx, gy, gz, r0, r1, r2, wm1, hm1).valid ? 1 : 0;
+    }
+  }
+  cnt_out[n] = (float)cnt;
+}
+
+// One thread per (voxel, view) pair: blockIdx.y = view for y < V.  Short dependency chains and N*V-way
+// parallelism instead of a 9-deep serial loop per voxel (these passes are latency-bound at fragment size).
+//   FILL = false: histogram the valid samples per bilinear cell (integer RED); the extra grid rows y >= V
+//                 compute ghat[n,c] = grad_out[n,c] / max(count[n],1) (div backward of back_project.py:72),
+//                 re-packed to 16-byte aligned rows of C floats, one element per thread-iteration.
+//   FILL = true : claim a slot in the cell (integer atomic), store {n, fx, fy}.
+template <int KIND, bool FILL>
+__global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const BwdParams p) {
+  const int v = blockIdx.y;
+  if (!FILL && v >= p.V) {
+    const int C = p.C, C1 = C + 1;
+    const int64_t total = p.N * C;
+    const int64_t blk = (int64_t)(v - p.V) * gridDim.x + blockIdx.x;
+    const int64_t base = blk * (kSampleThreads * kGhatPerThread) + threadIdx.x;
+    float g[kGhatPerThread], d[kGhatPerThread];
+#pragma unroll
+    for (int k = 0; k < kGhatPerThread; ++k) {  // all loads first
+      const int64_t i = base + (int64_t)k * kSampleThreads;
+      g[k] = 0.f; d[k] = 1.f;
+      if (i < total) {
+        const int64_t r = i / C;
+        const int c = (int)(i - r * C);
+        g[k] = __ldg(p.grad_out + r * C1 + c);
+        d[k] = fmaxf(__ldg(p.count + r), 1.0f);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < kGhatPerThread; ++k) {
+      const int64_t i = base + (int64_t)k * kSampleThreads;
+      if (i < total) p.ghat[i] = __fdiv_rn(g[k], d[k]);
+    }
+    return;
+  }
+  const int64_t n = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
+  if (n >= p.N) return;
+  float cx, cy, cz;
+  const int b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
+  if (b < 0) return;
   float gx, gy, gz;
   const float* o = p.origin + 3 * b;
   voxel_world(cx, cy, cz, p.vs, __ldg(o), __ldg(o + 1), __ldg(o + 2), gx, gy, gz);
-  const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
-  int cnt = 0;
-  for (int v = 0; v < p.V; ++v) {
-    float4 r0, r1, r2;
-    load_krcam(p.KR, v, p.B, b, r0, r1, r2);
-    const Sample s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
-    if (s.valid) {
-      ++cnt;
-      const int key = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
-      if (!FILL) {
-        atomicAdd(bin_cnt + key, 1);
-      } else {
-        const int slot = atomicSub(bin_cnt + key, 1) - 1;  // counts back to zero; order fixed later by `order`
-        const int pos = __ldg(p.bin_start + key) + slot;
-        p.entries[pos] = make_int4((int)n, __float_as_int(s.fx), __float_as_int(s.fy), 0);
-      }
-    }
-  }
-  return cnt;
-}
-
-template <int KIND>
-__global__ void __launch_bounds__(kPrepThreads) bp_bwd_prep_kernel(const BwdParams p) {
-  __shared__ float s_div[kPrepThreads];
-  const int tid = threadIdx.x;
-  const int64_t n0 = (int64_t)blockIdx.x * kPrepThreads;
-  const int64_t n = n0 + tid;
-  if (blockIdx.x == 0 && tid == 0) *p.counter = 0u;
-  int cnt = 0;
-  if (n < p.N) cnt = project_all_views<KIND, false>(p, n, p.bin_cnt);
-  s_div[tid] = (float)max(cnt, 1);
-  __syncthreads();
-  // ghat[n, c] = grad_out[n, c] / max(count, 1)   (div backward of back_project.py:72), rows re-packed to C floats
-  const int C = p.C, C1 = C + 1;
-  const int rows = (int)min((int64_t)kPrepThreads, p.N - n0);
-  const float* __restrict__ go = p.grad_out + n0 * C1;
-  float* __restrict__ gh = p.ghat + n0 * C;
-  int r = tid / C, c = tid - r * C;
-  const int dr = kPrepThreads / C, dc = kPrepThreads - dr * C;
-  for (int i = tid; i < rows * C; i += kPrepThreads) {
-    gh[i] = __fdiv_rn(__ldg(go + r * C1 + c), s_div[r]);
-    r += dr; c += dc;
-    if (c >= C) { c -= C; ++r; }
+  float4 r0, r1, r2;
+  load_krcam(p.KR, v, p.B, b, r0, r1, r2);
+  const Sample s = project(gx, gy, gz, r0, r1, r2, (float)(p.W - 1), (float)(p.H - 1));
+  if (!s.valid) return;
+  const int key = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
+  if (!FILL) {
+    atomicAdd(p.bin_cnt + key, 1);
+  } else {
+    const int slot = atomicSub(p.bin_cnt + key, 1) - 1;  // counts back to zero; order fixed later by `order`
+    const int pos = __ldg(p.bin_start + key) + slot;
+    p.entries[pos] = make_int4((int)n, __float_as_int(s.fx), __float_as_int(s.fy), 0);
   }
 }
 
-template <int KIND>
-__global__ void __launch_bounds__(kPrepThreads) bp_bwd_fill_kernel(const BwdParams p) {
-  const int64_t n = (int64_t)blockIdx.x * kPrepThreads + threadIdx.x;
-  if (n < p.N) project_all_views<KIND, true>(p, n, p.bin_cnt);
-}
-
-// ---- exclusive scan of the cell histogram ------------------------------------------------------
-__global__ void __launch_bounds__(kScanThreads) bp_scan_sums_kernel(const BwdParams p) {
+// ---- exclusive scan of the cell histogram: ONE pass, chained look-back ---------------------------
+// CTAs take chunk ids from a ticket (so a chunk's predecessors are always already scheduled), publish their
+// aggregate, walk back over predecessors until they meet an inclusive prefix, then publish their own.
+// state word = (flag << 32) | value, flag 0 = not ready, 1 = aggregate, 2 = inclusive prefix.  Integer sums:
+// the result does not depend on the order in which CTAs arrive.
+__global__ void __launch_bounds__(kScanThreads) bp_scan_kernel(const BwdParams p) {
   __shared__ int red[kScanThreads / 32];
-  __shared__ bool s_last;
+  __shared__ int s_cid, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int64_t base = (int64_t)blockIdx.x * kScanChunk;
-  int s = 0;
-  for (int i = 0; i < kScanItems; ++i) {
-    const int64_t idx = base + (int64_t)i * kScanThreads + tid;
-    if (idx < p.M) s += p.bin_cnt[idx];
-  }
-  s = __reduce_add_sync(kFullB, s);
-  if (lane == 0) red[warp] = s;
+  if (tid == 0) s_cid = (int)atomicAdd(p.counter, 1u);
   __syncthreads();
-  if (tid == 0) {
-    int t = 0;
-    for (int w = 0; w < kScanThreads / 32; ++w) t += red[w];
-    p.chunk_sums[blockIdx.x] = t;
-    __threadfence();
-    s_last = (atomicAdd(p.counter, 1u) == (unsigned)(gridDim.x - 1));
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  // last CTA: exclusive scan of the chunk sums in place (integers: order-independent), total -> bin_start[M]
-  __shared__ int carry;
-  if (tid == 0) carry = 0;
-  __syncthreads();
-  volatile int* cs = p.chunk_sums;
-  for (int c0 = 0; c0 < p.nchunks; c0 += kScanThreads) {
-    const int i = c0 + tid;
-    const int v = (i < p.nchunks) ? cs[i] : 0;
-    int inc = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int t = __shfl_up_sync(kFullB, inc, o);
-      if (lane >= o) inc += t;
-    }
-    if (lane == 31) red[warp] = inc;
-    __syncthreads();
-    int woff = 0;
-    for (int w = 0; w < warp; ++w) woff += red[w];
-    int tot = 0;
-    for (int w = 0; w < kScanThreads / 32; ++w) tot += red[w];
-    if (i < p.nchunks) cs[i] = carry + woff + inc - v;
-    __syncthreads();
-    if (tid == 0) carry += tot;
-    __syncthreads();
-  }
-  if (tid == 0) p.bin_start[p.M] = carry;
-}
-
-__global__ void __launch_bounds__(kScanThreads) bp_scan_apply_kernel(const BwdParams p) {
-  __shared__ int red[kScanThreads / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // thread owns kScanItems consecutive cells
-  const int64_t base = (int64_t)blockIdx.x * kScanChunk + (int64_t)tid * kScanItems;
+  const int cid = s_cid;
+  const int64_t base = (int64_t)cid * kScanChunk + (int64_t)tid * kScanItems;
   int v[kScanItems];
+  if (base + kScanItems <= p.M) {
+    const int4* q = reinterpret_cast<const int4*>(p.bin_cnt + base);
+#pragma unroll
+    for (int i = 0; i < kScanItems / 4; ++i) {
+      const int4 t = q[i];
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) v[i] = (base + i < p.M) ? p.bin_cnt[base + i] : 0;
+  }
   int s = 0;
 #pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    v[i] = (base + i < p.M) ? p.bin_cnt[base + i] : 0;
-    s += v[i];
-  }
+  for (int i = 0; i < kScanItems; ++i) s += v[i];
   int inc = s;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -179,8 +164,35 @@ __global__ void __launch_bounds__(kScanThreads) bp_scan_apply_kernel(const BwdPa
   }
   if (lane == 31) red[warp] = inc;
   __syncthreads();
-  int off = p.chunk_sums[blockIdx.x] + inc - s;
-  for (int w = 0; w < warp; ++w) off += red[w];
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    if (w < warp) woff += red[w];
+    total += red[w];
+  }
+  if (tid == 0) {
+    volatile unsigned long long* st = p.scan_state;
+    int prefix = 0;
+    if (cid == 0) {
+      st[0] = (2ull << 32) | (unsigned)total;
+    } else {
+      st[cid] = (1ull << 32) | (unsigned)total;
+      __threadfence();
+      int j = cid - 1;
+      while (true) {
+        unsigned long long w;
+        do { w = st[j]; } while ((w >> 32) == 0ull);
+        prefix += (int)(unsigned)(w & 0xffffffffull);
+        if ((w >> 32) == 2ull) break;
+        --j;
+      }
+      st[cid] = (2ull << 32) | (unsigned)(prefix + total);
+    }
+    s_prefix = prefix;
+    if (cid == gridDim.x - 1) p.bin_start[p.M] = prefix + total;
+  }
+  __syncthreads();
+  int off = s_prefix + woff + inc - s;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     if (base + i < p.M) p.bin_start[base + i] = off;
@@ -228,9 +240,8 @@ __device__ __forceinline__ void bitonic_cell(volatile int4* E, int k, int lane) 
   }
 }
 
-constexpr int kOrderBinsPerTask = 1024;
 
-__global__ void __launch_bounds__(256) bp_bwd_order_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(256) bp_bwd_order_kernel(const BwdParams p, const int kOrderBinsPerTask) {
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -333,8 +344,23 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_kernel(const 
       }
     }
     if (gvalid) {
+      if (!p.grad_nchw) {
 #pragma unroll
-      for (int i = 0; i < R; ++i) grad4[t * C4 + i * G + gl] = acc[i];
+        for (int i = 0; i < R; ++i) grad4[t * C4 + i * G + gl] = acc[i];
+      } else {
+        // (V,B,C,H,W): texel t = (vb, y, x) -> channel c lives at ((vb*C + c)*H + y)*W + x
+        const int64_t hw = (int64_t)p.H * p.W;
+        const int64_t vb = t / hw, yx = t - vb * hw;
+        float* dst = p.grad_feats + vb * p.C * hw + yx;
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const int c0 = (i * G + gl) * 4;
+          dst[(int64_t)(c0 + 0) * hw] = acc[i].x;
+          dst[(int64_t)(c0 + 1) * hw] = acc[i].y;
+          dst[(int64_t)(c0 + 2) * hw] = acc[i].z;
+          dst[(int64_t)(c0 + 3) * hw] = acc[i].w;
+        }
+      }
     }
   }
 }
@@ -373,14 +399,22 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_generic_kerne
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int c = lane + 32 * i;
-      if (c < C) p.grad_feats[t * C + c] = acc[i];
+      if (c < C) {
+        if (!p.grad_nchw) {
+          p.grad_feats[t * C + c] = acc[i];
+        } else {
+          const int64_t hw = (int64_t)p.H * p.W;
+          const int64_t vb = t / hw, yx = t - vb * hw;
+          p.grad_feats[(vb * C + c) * hw + yx] = acc[i];
+        }
+      }
     }
   }
 }
 
 // ---- host ----------------------------------------------------------------------------------------
 struct BwdWs {
-  size_t ghat, bin_cnt, bin_start, chunk_sums, counter, entries, total;
+  size_t ghat, cnt, bin_cnt, bin_start, scan_state, counter, entries, total, zero_bytes;
   int nchunks;
   int64_t M;
 };
@@ -392,10 +426,12 @@ static BwdWs bwd_ws_layout(int64_t N, int B, int V, int C, int H, int W) {
   size_t o = 0;
   const size_t n1 = (size_t)(N > 0 ? N : 1);
   w.ghat = o; o = align_up(o + sizeof(float) * n1 * (size_t)C, 256);
+  w.cnt = o; o = align_up(o + sizeof(float) * n1, 256);
   w.bin_cnt = o; o = align_up(o + sizeof(int) * (size_t)w.M, 256);
-  w.bin_start = o; o = align_up(o + sizeof(int) * (size_t)(w.M + 1), 256);
-  w.chunk_sums = o; o = align_up(o + sizeof(int) * (size_t)(w.nchunks + 1), 256);
+  w.scan_state = o; o = align_up(o + sizeof(unsigned long long) * (size_t)(w.nchunks + 1), 256);
   w.counter = o; o = align_up(o + 256, 256);
+  w.zero_bytes = o - w.bin_cnt;  // bin_cnt, scan_state and the ticket are cleared by ONE memset
+  w.bin_start = o; o = align_up(o + sizeof(int) * (size_t)(w.M + 1), 256);
   w.entries = o; o = align_up(o + sizeof(int4) * n1 * (size_t)V, 256);
   w.total = o;
   return w;
@@ -427,26 +463,44 @@ static gather_kernel_t pick_gather_kernel(int C, int& NG) {
 }
 
 template <int KIND>
-static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
+static int launch_bwd(const BwdParams& p, size_t zero_bytes, float* cnt_ws, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  D3M_CUDA_CHECK(cudaMemsetAsync(p.bin_cnt, 0, sizeof(int) * (size_t)p.M, stream));
-  const unsigned vox_ctas = (unsigned)((p.N + kPrepThreads - 1) / kPrepThreads);
-  bp_bwd_prep_kernel<KIND><<<vox_ctas, kPrepThreads, 0, stream>>>(p);
-  D3M_CUDA_CHECK(cudaGetLastError());
-  bp_scan_sums_kernel<<<p.nchunks, kScanThreads, 0, stream>>>(p);
-  D3M_CUDA_CHECK(cudaGetLastError());
-  bp_scan_apply_kernel<<<p.nchunks, kScanThreads, 0, stream>>>(p);
-  D3M_CUDA_CHECK(cudaGetLastError());
-  bp_bwd_fill_kernel<KIND><<<vox_ctas, kPrepThreads, 0, stream>>>(p);
+  D3M_CUDA_CHECK(cudaMemsetAsync(p.bin_cnt, 0, zero_bytes, stream));
+  const unsigned vox_ctas = (unsigned)((p.N + kSampleThreads - 1) / kSampleThreads);
+  if (cnt_ws) {  // no forward count handed over: recompute it
+    LaunchScope ls("bp_bwd_count", stream);
+    bp_bwd_count_kernel<KIND><<<vox_ctas, kSampleThreads, 0, stream>>>(p, cnt_ws);
+  }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
-    const int64_t ntasks = (p.M + kOrderBinsPerTask - 1) / kOrderBinsPerTask;
+    const int64_t ghat_blocks = (p.N * p.C + kSampleThreads * kGhatPerThread - 1) / (kSampleThreads * kGhatPerThread);
+    const unsigned ghat_rows = (unsigned)((ghat_blocks + vox_ctas - 1) / vox_ctas);
+    LaunchScope ls("bp_bwd_hist_ghat", stream);
+    bp_bwd_sample_kernel<KIND, false><<<dim3(vox_ctas, p.V + ghat_rows), kSampleThreads, 0, stream>>>(p);
+  }
+  D3M_CUDA_CHECK(cudaGetLastError());
+  {
+    LaunchScope ls("bp_bwd_scan", stream);
+    bp_scan_kernel<<<p.nchunks, kScanThreads, 0, stream>>>(p);
+  }
+  D3M_CUDA_CHECK(cudaGetLastError());
+  {
+    LaunchScope ls("bp_bwd_fill", stream);
+    bp_bwd_sample_kernel<KIND, true><<<dim3(vox_ctas, p.V), kSampleThreads, 0, stream>>>(p);
+  }
+  D3M_CUDA_CHECK(cudaGetLastError());
+  {
+    // cells per warp task: small enough that even the coarsest level spreads over every SM
+    int bins = (int)(p.M / ((int64_t)sms * 32));
+    bins = bins < 8 ? 8 : (bins > 256 ? 256 : bins);
+    const int64_t ntasks = (p.M + bins - 1) / bins;
     int64_t ctas = (ntasks + 7) / 8;
-    if (ctas > (int64_t)sms * 8) ctas = (int64_t)sms * 8;
+    if (ctas > (int64_t)sms * 64) ctas = (int64_t)sms * 64;
     if (ctas < 1) ctas = 1;
-    bp_bwd_order_kernel<<<(unsigned)ctas, 256, 0, stream>>>(p);
+    LaunchScope ls("bp_bwd_order", stream);
+    bp_bwd_order_kernel<<<(unsigned)ctas, 256, 0, stream>>>(p, bins);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
   {
@@ -461,6 +515,7 @@ static int launch_bwd(const BwdParams& p, cudaStream_t stream) {
     int64_t ctas = (nsteps + kGatherWarps - 1) / kGatherWarps;
     if (ctas > (int64_t)sms * 16) ctas = (int64_t)sms * 16;
     if (ctas < 1) ctas = 1;
+    LaunchScope ls("bp_bwd_gather", stream);
     k<<<(unsigned)ctas, kGatherWarps * 32, 0, stream>>>(p);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
@@ -478,8 +533,8 @@ extern "C" size_t d3m_back_project_bwd_workspace(int64_t N, int B, int V, int C,
 
 extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                                     float voxel_size, int V, int C, int H, int W, const float* KRcam,
-                                    const float* grad_out, float* grad_feats_nhwc, void* workspace,
-                                    size_t workspace_bytes, void* stream_) {
+                                    const float* grad_out, const float* count, float* grad_feats_nhwc, int grad_nchw,
+                                    void* workspace, size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE,
               "back_project backward: no CUDA device (there is no CPU fallback)");
@@ -487,6 +542,7 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
               "back_project backward: bad sizes N=%lld B=%d V=%d C=%d H=%d W=%d", (long long)N, B, V, C, H, W);
   D3M_REQUIRE(coords_kind >= 0 && coords_kind <= 2, D3M_ERR_ARG, "back_project backward: coords_kind=%d", coords_kind);
   D3M_REQUIRE((int64_t)V * B * H * W < (1ll << 30), D3M_ERR_ARG, "back_project backward: V*B*H*W must be < 2^30");
+  D3M_REQUIRE(V <= 65535 - 4096, D3M_ERR_ARG, "back_project backward: too many views");
   D3M_REQUIRE(N * (int64_t)V < (1ll << 31), D3M_ERR_ARG, "back_project backward: N*V must be < 2^31 samples");
   D3M_REQUIRE(grad_feats_nhwc && workspace, D3M_ERR_ARG, "back_project backward: NULL pointer");
   const BwdWs w = bwd_ws_layout(N, B, V, C, H, W);
@@ -506,13 +562,16 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
   p.ghat = reinterpret_cast<float*>(ws + w.ghat);
   p.bin_cnt = reinterpret_cast<int*>(ws + w.bin_cnt);
   p.bin_start = reinterpret_cast<int*>(ws + w.bin_start);
-  p.chunk_sums = reinterpret_cast<int*>(ws + w.chunk_sums);
+  p.scan_state = reinterpret_cast<unsigned long long*>(ws + w.scan_state);
   p.counter = reinterpret_cast<unsigned int*>(ws + w.counter);
   p.entries = reinterpret_cast<int4*>(ws + w.entries);
   p.grad_feats = grad_feats_nhwc;
   p.M = w.M;
   p.nchunks = w.nchunks;
-  if (coords_kind == D3M_COORDS_F32) return launch_bwd<D3M_COORDS_F32>(p, stream);
-  if (coords_kind == D3M_COORDS_I64) return launch_bwd<D3M_COORDS_I64>(p, stream);
-  return launch_bwd<D3M_COORDS_I32>(p, stream);
+  p.grad_nchw = grad_nchw ? 1 : 0;
+  float* cnt_ws = count ? nullptr : reinterpret_cast<float*>(ws + w.cnt);
+  p.count = count ? count : cnt_ws;
+  if (coords_kind == D3M_COORDS_F32) return launch_bwd<D3M_COORDS_F32>(p, w.zero_bytes, cnt_ws, stream);
+  if (coords_kind == D3M_COORDS_I64) return launch_bwd<D3M_COORDS_I64>(p, w.zero_bytes, cnt_ws, stream);
+  return launch_bwd<D3M_COORDS_I32>(p, w.zero_bytes, cnt_ws, stream);
 }

@@ -499,7 +499,10 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   const int64_t cap = (int64_t)sms * 32;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
-  k<<<(unsigned)ctas, kFwdWarps * 32, smem, stream>>>(p);
+  {
+    LaunchScope ls("bp_fwd", stream);
+    k<<<(unsigned)ctas, kFwdWarps * 32, smem, stream>>>(p);
+  }
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
 }
@@ -551,9 +554,15 @@ extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t
   sp.partial = reinterpret_cast<double*>(ws + w.partial);
   sp.stats = reinterpret_cast<float*>(ws + w.stats);
   sp.counter = p.counter;
-  bp_stats_kernel<<<w.nchunks, kStatsThreads, 0, stream>>>(sp);
+  {
+    LaunchScope ls("bp_fwd_stats", stream);
+    bp_stats_kernel<<<w.nchunks, kStatsThreads, 0, stream>>>(sp);
+  }
   D3M_CUDA_CHECK(cudaGetLastError());
-  bp_normalise_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(p.zbar, p.bidx, sp.stats, out, N, C + 1);
+  {
+    LaunchScope ls("bp_fwd_normalise", stream);
+    bp_normalise_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(p.zbar, p.bidx, sp.stats, out, N, C + 1);
+  }
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
 }

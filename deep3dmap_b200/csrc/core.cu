@@ -2,6 +2,12 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
 #include "d3m_common.cuh"
 
 namespace d3m {
@@ -18,6 +24,32 @@ void set_error(const char* fmt, ...) {
 int cuda_fail(cudaError_t e, const char* what) {
   set_error("CUDA error %d (%s) in %s", (int)e, cudaGetErrorString(e), what);
   return D3M_ERR_CUDA + (int)e;
+}
+
+static std::atomic<long long> g_launches{0};
+static std::atomic<bool> g_profiling{false};
+static std::mutex g_prof_mu;
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+
+LaunchScope::LaunchScope(const char* name, cudaStream_t stream) : name_(name), stream_(stream), start_(nullptr) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_profiling.load(std::memory_order_relaxed)) {
+    if (cudaEventCreate(&start_) == cudaSuccess) cudaEventRecord(start_, stream_);
+    else start_ = nullptr;
+  }
+}
+
+LaunchScope::~LaunchScope() {
+  if (!start_) return;
+  cudaEvent_t stop = nullptr;
+  if (cudaEventCreate(&stop) == cudaSuccess) {
+    cudaEventRecord(stop, stream_);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back({name_, start_, stop});
+  } else {
+    cudaEventDestroy(start_);
+  }
 }
 
 // (n_maps, A, Bn) -> (n_maps, Bn, A) through a padded 32x32 shared-memory tile: both sides coalesced.
@@ -49,6 +81,7 @@ static int transpose_maps(const float* src, float* dst, int64_t n_maps, int A, i
   for (int64_t m0 = 0; m0 < n_maps; m0 += 65535) {
     const unsigned nz = (unsigned)((n_maps - m0) < 65535 ? (n_maps - m0) : 65535);
     dim3 grid((Bn + 31) / 32, (A + 31) / 32, nz);
+    LaunchScope ls("relayout_transpose", stream);
     transpose_maps_kernel<<<grid, 256, 0, stream>>>(src + m0 * (int64_t)A * Bn, dst + m0 * (int64_t)A * Bn, A, Bn);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
@@ -68,6 +101,47 @@ extern "C" int d3m_device_count(void) {
     return 0;
   }
   return n;
+}
+
+extern "C" int64_t d3m_kernel_launches(void) { return (int64_t)d3m::g_launches.load(); }
+
+extern "C" int d3m_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(d3m::g_prof_mu);
+  for (auto& r : d3m::g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  d3m::g_prof.clear();
+  d3m::g_profiling.store(true);
+  return D3M_OK;
+}
+
+extern "C" int d3m_profile_end(char* json_out, size_t cap) {
+  d3m::g_profiling.store(false);
+  std::lock_guard<std::mutex> lk(d3m::g_prof_mu);
+  std::map<std::string, std::pair<long long, double>> agg;
+  for (auto& r : d3m::g_prof) {
+    float ms = 0.f;
+    cudaEventSynchronize(r.b);
+    if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+      auto& e = agg[r.name];
+      e.first += 1;
+      e.second += ms;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  d3m::g_prof.clear();
+  std::string js = "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    char buf[256];
+    snprintf(buf, sizeof(buf), "%s\"%s\": {\"n\": %lld, \"ms\": %.6f}", first ? "" : ", ", kv.first.c_str(),
+             kv.second.first, kv.second.second);
+    js += buf;
+    first = false;
+  }
+  js += "}";
+  D3M_REQUIRE(json_out && cap > js.size(), D3M_ERR_ARG, "profile_end: buffer too small (%zu needed)", js.size() + 1);
+  memcpy(json_out, js.c_str(), js.size() + 1);
+  return D3M_OK;
 }
 
 extern "C" int d3m_feats_nchw_to_nhwc(const float* src, float* dst, int64_t n_maps, int C, int H, int W, void* stream) {

@@ -25,6 +25,16 @@ int cuda_fail(cudaError_t e, const char* what);
     }                                  \
   } while (0)
 
+// RAII marker around one kernel launch: counts it and, while profiling is on, brackets it with CUDA events
+// recorded on the launching stream (bench.py's live per-kernel timing).
+struct LaunchScope {
+  LaunchScope(const char* name, cudaStream_t stream);
+  ~LaunchScope();
+  const char* name_;
+  cudaStream_t stream_;
+  cudaEvent_t start_;
+};
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 __host__ __device__ static inline int align_up_dev(int x) { return (x + 15) & ~15; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }

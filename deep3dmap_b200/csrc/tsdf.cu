@@ -403,11 +403,15 @@ static int tsdf_launch(d3m_tsdf* h, const float* depth, const float* cimg, int F
   p.vs = h->vs; p.trunc = h->trunc;
   p.frames = d_frames; p.F = F; p.depth = depth; p.cimg = cimg; p.H = H; p.W = W;
   p.partial_max = h->d_partial;
-  tsdf_prep_kernel<<<dim3(kPrepParts, F), 256, 0, stream>>>(depth, H * W, h->d_partial);
+  {
+    LaunchScope ls("tsdf_prep", stream);
+    tsdf_prep_kernel<<<dim3(kPrepParts, F), 256, 0, stream>>>(depth, H * W, h->d_partial);
+  }
   D3M_CUDA_CHECK(cudaGetLastError());
   const int sem = flags & 1;
   const bool color = (flags & D3M_TSDF_WITH_COLOR) && cimg != nullptr && sem == D3M_TSDF_KERNEL_SEMANTICS;
   const int grid = h->sms * 4;
+  LaunchScope ls("tsdf_integrate", stream);
   if (sem == D3M_TSDF_KERNEL_SEMANTICS) {
     if (color) tsdf_integrate_kernel<D3M_TSDF_KERNEL_SEMANTICS, true><<<grid, kTsdfThreads, 0, stream>>>(p);
     else tsdf_integrate_kernel<D3M_TSDF_KERNEL_SEMANTICS, false><<<grid, kTsdfThreads, 0, stream>>>(p);
@@ -490,7 +494,10 @@ extern "C" int d3m_tsdf_reset(d3m_tsdf* h, void* stream_) {
   D3M_REQUIRE(h, D3M_ERR_ARG, "tsdf_reset: NULL handle");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   D3M_CUDA_CHECK(cudaSetDevice(h->device));
-  fill_kernel<<<h->sms * 8, 256, 0, stream>>>(h->tsdf, 1.0f, (int64_t)h->nvox);  // tsdf_volume.py:50
+  {
+    LaunchScope ls("tsdf_fill", stream);
+    fill_kernel<<<h->sms * 8, 256, 0, stream>>>(h->tsdf, 1.0f, (int64_t)h->nvox);
+  }  // tsdf_volume.py:50
   D3M_CUDA_CHECK(cudaGetLastError());
   D3M_CUDA_CHECK(cudaMemsetAsync(h->weight, 0, h->nvox * 4, stream));
   D3M_CUDA_CHECK(cudaMemsetAsync(h->color, 0, h->nvox * 4, stream));

@@ -26,6 +26,35 @@ def _stream(device):
     return torch.cuda.current_stream(device).cuda_stream
 
 
+class _on_device:
+    """`with torch.cuda.device(dev)` costs ~10 us of host time; skip it when `dev` already is current."""
+
+    def __init__(self, dev):
+        self.ctx = None if torch.cuda.current_device() == dev.index else torch.cuda.device(dev)
+
+    def __enter__(self):
+        if self.ctx is not None:
+            self.ctx.__enter__()
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+
+
+_ws_cache = {}
+
+
+def _workspace(kind, key, dev):
+    """Workspace byte count is a pure function of the shapes: cache the ctypes query; the buffer itself comes
+    from torch's caching allocator (stream-ordered reuse, graph-capture safe)."""
+    n = _ws_cache.get((kind,) + key)
+    if n is None:
+        L = _lib.lib()
+        n = L.d3m_back_project_fwd_workspace(*key) if kind == "f" else L.d3m_back_project_bwd_workspace(*key)
+        _ws_cache[(kind,) + key] = n
+    return torch.empty((n,), dtype=torch.uint8, device=dev), n
+
+
 def feats_to_channels_last(feats):
     """(V,B,C,H,W) -> channels-last storage (V,B,H,W,C); zero-copy when `feats` already is a permuted view."""
     if feats.dim() != 5:
@@ -53,15 +82,22 @@ def feats_to_nchw(g_nhwc):
     return out
 
 
+def _as(t, device, dtype):
+    if t.device != device or t.dtype != dtype:
+        t = t.to(device=device, dtype=dtype)
+    return t if t.is_contiguous() else t.contiguous()
+
+
 def _prep_small(coords, origin, KRcam, device):
     if coords.dim() != 2 or coords.shape[1] != 4:
         raise ValueError("coords must be (num_voxels, 4) [batch, x, y, z]")
     if coords.dtype not in _COORD_KIND:
         coords = coords.float()
-    coords = coords.contiguous()
-    origin = origin.to(device=device, dtype=torch.float32).contiguous()
-    KRcam = KRcam.to(device=device, dtype=torch.float32).contiguous()
-    return coords, origin, KRcam
+    if coords.device != device:
+        coords = coords.to(device)
+    if not coords.is_contiguous():
+        coords = coords.contiguous()
+    return coords, _as(origin, device, torch.float32), _as(KRcam, device, torch.float32)
 
 
 def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam):
@@ -76,9 +112,8 @@ def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam):
     count = torch.empty((N,), dtype=torch.float32, device=dev)
     if N == 0:
         return out, count
-    ws_bytes = L.d3m_back_project_fwd_workspace(N, B, V, C)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    ws, ws_bytes = _workspace("f", (N, B, V, C), dev)
+    with _on_device(dev):
         rc = L.d3m_back_project_fwd(coords.data_ptr(), _COORD_KIND[coords.dtype], N, origin.data_ptr(), B,
                                     float(voxel_size), feats_nhwc.data_ptr(), V, C, H, W, KRcam.data_ptr(),
                                     out.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev))
@@ -86,21 +121,21 @@ def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam):
     return out, count
 
 
-def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, grad_out):
-    """Kernel-level backward: grad_out (N,C+1) -> grad of the channels-last maps (V,B,H,W,C)."""
+def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, grad_out, nchw=False, count=None):
+    """Kernel-level backward: grad_out (N,C+1) -> grad of the maps, channels-last (V,B,H,W,C) or, with
+    nchw=True, in the reference layout (V,B,C,H,W) written directly by the gather kernel."""
     L = _lib.lib()
     dev = grad_out.device
     V, B, H, W, C = feats_shape_nhwc
     N = coords.shape[0]
-    grad = torch.empty((V, B, H, W, C), dtype=torch.float32, device=dev)
+    grad = torch.empty((V, B, C, H, W) if nchw else (V, B, H, W, C), dtype=torch.float32, device=dev)
     if grad.numel() == 0:
         return grad
-    ws_bytes = L.d3m_back_project_bwd_workspace(N, B, V, C, H, W)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=dev)
-    with torch.cuda.device(dev):
+    ws, ws_bytes = _workspace("b", (N, B, V, C, H, W), dev)
+    with _on_device(dev):
         rc = L.d3m_back_project_bwd(_ptr(coords), _COORD_KIND[coords.dtype], N, _ptr(origin), B, float(voxel_size),
-                                    V, C, H, W, _ptr(KRcam), _ptr(grad_out), grad.data_ptr(), ws.data_ptr(),
-                                    ws_bytes, _stream(dev))
+                                    V, C, H, W, _ptr(KRcam), _ptr(grad_out), _ptr(count), grad.data_ptr(), 1 if nchw else 0,
+                                    ws.data_ptr(), ws_bytes, _stream(dev))
     _lib.check(rc, "d3m_back_project_bwd")
     return grad
 
@@ -110,31 +145,31 @@ class _BackProject(torch.autograd.Function):
     def forward(ctx, feats, coords, origin, voxel_size, KRcam):
         if not feats.is_cuda:
             raise _lib.D3MError("back_project: feats must live on a CUDA device (no CPU fallback in this build)")
-        _lib.require_device()
         if feats.dtype != torch.float32:
             feats = feats.float()
         dev = feats.device
-        coords = coords.to(dev)
         coords, origin, KRcam = _prep_small(coords, origin, KRcam, dev)
         nhwc = feats_to_channels_last(feats)
         out, count = back_project_forward(coords, origin, voxel_size, nhwc, KRcam)
-        ctx.save_for_backward(coords, origin, KRcam)
+        ctx.save_for_backward(coords, origin, KRcam, count)
         ctx.voxel_size = float(voxel_size)
         ctx.nhwc_shape = tuple(nhwc.shape)
         ctx.mark_non_differentiable(count)
+        ctx.set_materialize_grads(False)
         return out, count
 
     @staticmethod
     def backward(ctx, grad_vol, grad_count):
-        coords, origin, KRcam = ctx.saved_tensors
+        coords, origin, KRcam, count = ctx.saved_tensors
         if not ctx.needs_input_grad[0]:
             return None, None, None, None, None
-        g = grad_vol.contiguous().float()
-        grad_nhwc = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g)
+        if grad_vol is None:
+            return None, None, None, None, None
+        g = grad_vol if (grad_vol.is_contiguous() and grad_vol.dtype == torch.float32) else grad_vol.contiguous().float()
         if GRAD_LAYOUT == "view":
-            grad = grad_nhwc.permute(0, 1, 4, 2, 3)
+            grad = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g, count=count).permute(0, 1, 4, 2, 3)
         else:
-            grad = feats_to_nchw(grad_nhwc)
+            grad = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g, nchw=True, count=count)
         return grad, None, None, None, None
 
 

@@ -49,6 +49,15 @@ const char* d3m_last_error(void);
 /* number of CUDA devices visible (0 when none / driver missing); never fails */
 int d3m_device_count(void);
 
+/* Diagnostics used by bench.py (not part of the reference surface).
+ *   d3m_kernel_launches: kernels this library has launched in this process since load.
+ *   d3m_profile_begin / d3m_profile_end: while enabled, one CUDA-event pair is recorded on the launching
+ *   stream around every kernel launch; _end synchronises, writes a JSON object
+ *   {"<kernel>": {"n": launches, "ms": total device milliseconds}, ...} into `json_out` and disables it. */
+int64_t d3m_kernel_launches(void);
+int d3m_profile_begin(void);
+int d3m_profile_end(char* json_out, size_t cap);
+
 /* ---------------------------------------------------------------------------------------------
  * Feature-map layout.  The kernels read / write per-view maps channels-last: (V,B,H,W,C) so that one
  * texel is C contiguous floats (128-bit loads).  The reference hands over (V,B,C,H,W) as produced
@@ -79,13 +88,16 @@ int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const f
  * integer atomics only, each bin is ordered by voxel index, and every texel is accumulated by one
  * lane group in a fixed order -- no floating-point atomics anywhere.
  *   grad_out         (N,C+1) float32 (the depth column carries no gradient to feats)
- *   grad_feats_nhwc  (V,B,H,W,C) float32, fully overwritten
+ *   count            (N,) float32 as returned by d3m_back_project_fwd for the same inputs, or NULL
+ *                    (then the view counts are recomputed by one extra kernel)
+ *   grad_feats       float32, fully overwritten; (V,B,H,W,C) when grad_nchw == 0, the reference's
+ *                    (V,B,C,H,W) when grad_nchw != 0 (the gather kernel then stores channel-strided)
  * ------------------------------------------------------------------------------------------- */
 size_t d3m_back_project_bwd_workspace(int64_t N, int B, int V, int C, int H, int W);
 int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                          float voxel_size, int V, int C, int H, int W, const float* KRcam,
-                         const float* grad_out, float* grad_feats_nhwc, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         const float* grad_out, const float* count, float* grad_feats, int grad_nchw,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * TSDF fusion  (replaces TSDFVolume, tsdf_volume.py:10-307, and TSDFVolumeTorch :485-574)

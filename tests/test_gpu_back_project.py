@@ -164,3 +164,21 @@ def test_batched_fragments_equal_individual_calls():
                                 t(inp["KRcam"][:, b:b + 1].copy()))
         mm = torch.from_numpy(m).to(dev)
         assert torch.equal(vol[mm], vb) and torch.equal(cnt[mm], cntb)
+
+
+def test_backward_without_forward_count_recomputes_it():
+    """C ABI contract: `count` is optional in d3m_back_project_bwd; both paths give identical bits, in both layouts."""
+    from deep3dmap_b200 import voxel
+    inp = cases.bp_level(1, 7000, np.int64)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    coords, origin, KR, go = t(inp["coords"]), t(inp["origin"]), t(inp["KRcam"]), t(inp["grad_out"])
+    nhwc = voxel.feats_to_channels_last(t(inp["feats"]))
+    vol, cnt = voxel.back_project_forward(coords, origin, 0.04, nhwc, KR)
+    shape = tuple(nhwc.shape)
+    g1 = voxel.back_project_backward(coords, origin, 0.04, shape, KR, go, count=cnt)
+    g2 = voxel.back_project_backward(coords, origin, 0.04, shape, KR, go, count=None)
+    g3 = voxel.back_project_backward(coords, origin, 0.04, shape, KR, go, nchw=True, count=cnt)
+    assert torch.equal(g1, g2)
+    assert torch.equal(g1.permute(0, 1, 4, 2, 3), g3)
+    assert torch.equal(voxel.feats_to_nchw(g1), g3)
