@@ -254,30 +254,55 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         if args.profile_step == "tsdf":
             bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=True)
+        if args.profile_step == "dense":
+            bench_dense_l2(torch, dev, _lib, back_project, flush_buf, peak_gbs, args.steps, profile_only=True)
         return
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     # ---- timed region 1: inputs resident in HBM, L2 flushed between steps ---------------------------
+    # The step (3 x fwd+bwd, ~34 kernels of 5-60 us) is launch-bound from Python (host issue time ~ GPU time), so
+    # the whole step is captured once into a CUDA graph and replayed; the eager number is reported next to it.
+    def timed(run_step):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        barrier()
+        for a, b in ev:
+            flush_buf.fill_(1)
+            a.record()
+            run_step()
+            b.record()
+        barrier()
+        return float(np.mean([a.elapsed_time(b) for a, b in ev]))
+
     launches0 = _lib.kernel_launches()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    barrier()
-    for a, b in ev:
-        flush_buf.fill_(1)
-        a.record()
-        step_resident()
-        b.record()
-    barrier()
-    ms_steps = [a.elapsed_time(b) for a, b in ev]
-    # host-side issue cost of one step (python + ctypes + launches), GPU idle at start
+    ms_eager = timed(step_resident)
+    launches = _lib.kernel_launches() - launches0
+    graph, graph_err = None, None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                step_resident()
+            torch.cuda.current_stream().wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                step_resident()
+            for _ in range(3):
+                graph.replay()
+            torch.cuda.synchronize()
+        except Exception as err:  # capture is an optimisation, never a requirement
+            graph, graph_err = None, repr(err)[:200]
+            torch.cuda.synchronize()
+    ms_graph = timed(graph.replay) if graph is not None else None
+    ms_step = ms_graph if ms_graph is not None else ms_eager
+    # host-side issue cost of one eager step (python + autograd + ctypes + launches), GPU idle at start
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for _ in range(5):
         step_resident()
     host_ms = (time.perf_counter() - t0) / 5 * 1e3
     torch.cuda.synchronize()
-    launches = _lib.kernel_launches() - launches0
-    ms_step = float(np.mean(ms_steps))
 
     # ---- timed region 2 (e2e): host buffers in, host buffers out, through the public API ------------
     pin = []
@@ -346,6 +371,11 @@ def run_ours(args, rank, world, local_rank):
             per_level.append(acc)
         prof = per_level
 
+    # ---- large-volume leg: dense 96^3 level-2 call (BASELINE configs[0] shape, N = 884,736, 7.96 M samples) ----
+    dense = None
+    if rank == 0:
+        dense = bench_dense_l2(torch, dev, _lib, back_project, flush_buf, peak_gbs, args.steps)
+
     # ---- TSDF leg (rank 0 only; replicas only across ranks) -------------------------------------------
     tsdf = None
     if rank == 0:
@@ -409,6 +439,8 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e, "what": "back_project() public API from pinned host tensors; volume, count and "
                 "grad_feats copied back to pinned host memory every step"},
         "gpu_launches": int(launches), "host_issue_ms_per_step": host_ms,
+        "step_mode": "cuda_graph_replay" if ms_graph is not None else "eager", "ms_per_step_eager": ms_eager,
+        "ms_per_step_graph": ms_graph, "graph_error": graph_err,
         "roofline": {"bound": "hbm", "kernel": dom, "level": li, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg), "ms_per_launch": ms_k,
@@ -422,11 +454,66 @@ def run_ours(args, rank, world, local_rank):
         "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
                          "sample": "5 full steps of the same fragment on the host (OpenMP C port of the reference "
                                    "algorithm; %.1f ms/step)" % (cpu_sec * 1e3)},
+        "dense_level2": dense,
         "tsdf": tsdf,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_dense_l2(torch, dev, _lib, back_project, flush_buf, peak_gbs, steps, profile_only=False):
+    """Throughput-regime companion of the headline: one dense level-2 back_project call (96^3 voxels, C=24)."""
+    inp = synth.fragment_level_inputs(2)
+    C = synth.LEVELS[2]["C"]
+    N = inp["coords"].shape[0]
+    go = torch.from_numpy(synth.grad_out_for(N, C)).to(dev)
+    coords, origin, KR = (torch.from_numpy(inp[k]).to(dev) for k in ("coords", "origin", "KRcam"))
+    feats = torch.from_numpy(inp["feats"]).to(dev).requires_grad_(True)
+
+    def step():
+        feats.grad = None
+        vol, cnt = back_project(coords, origin, inp["voxel_size"], feats, KR)
+        vol.backward(go)
+        return cnt
+
+    for _ in range(3):
+        cnt = step()
+    torch.cuda.synchronize()
+    if profile_only:
+        flush_buf.fill_(1)
+        step()
+        torch.cuda.synchronize()
+        return None
+    S = int(cnt.sum().item())
+    ts = []
+    for _ in range(max(5, steps // 2)):
+        flush_buf.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    acc = {}
+    for _ in range(5):
+        flush_buf.fill_(1)
+        torch.cuda.synchronize()
+        _lib.profile_begin()
+        step()
+        for k, v in _lib.profile_end().items():
+            e = acc.setdefault(k, 0.0)
+            acc[k] = e + v["ms"] / 5
+    a_fwd, a_bwd = algorithmic_bytes(inp, S)
+    ms = float(np.mean(ts))
+    fwd_ms = acc.get("bp_fwd", 0.0)
+    gat_ms = acc.get("bp_bwd_gather", 0.0)
+    V, B, _, H, W = inp["feats"].shape
+    return {"N": int(N), "valid_samples": S, "samples_per_s": N * V / (ms * 1e-3), "ms_fwd_bwd": ms,
+            "algorithmic_bytes": int(a_fwd + a_bwd), "achieved_GBs": (a_fwd + a_bwd) / (ms * 1e-3) / 1e9,
+            "frac_of_measured_hbm_peak": (a_fwd + a_bwd) / (ms * 1e-3) / 1e9 / peak_gbs,
+            "frac_of_nominal_8TBs": (a_fwd + a_bwd) / (ms * 1e-3) / 1e9 / 8000.0,
+            "kernel_ms": {k: round(v, 4) for k, v in sorted(acc.items())},
+            "bp_fwd_GBs": a_fwd / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None,
+            "bp_bwd_gather_GBs": (16 * C * S + 4 * V * B * C * H * W + 16 * S) / (gat_ms * 1e-3) / 1e9 if gat_ms else None}
 
 
 def bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=False):
@@ -506,7 +593,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--profile-step", default="", choices=["", "bp", "tsdf"],
+    ap.add_argument("--no-graph", action="store_true", help="time the eager python path only")
+    ap.add_argument("--profile-step", default="", choices=["", "bp", "tsdf", "dense"],
                     help="profiler target: run only the hot-path steps (and the TSDF launches with 'tsdf'), print nothing")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

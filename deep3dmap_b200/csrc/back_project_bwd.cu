@@ -241,26 +241,32 @@ __device__ __forceinline__ void bitonic_cell(volatile int4* E, int k, int lane) 
 }
 
 
-__global__ void __launch_bounds__(256) bp_bwd_order_kernel(const BwdParams p, const int kOrderBinsPerTask) {
-  const int lane = threadIdx.x & 31;
+constexpr int kOrderWindow = 256;  // entries staged per warp (4 KB of shared memory)
+
+// Each warp owns a run of cells.  Per iteration it stages a window of whole cells (<= 32 cells, <= 256 entries)
+// in shared memory, ranks every entry inside its own cell by counting smaller voxel indices (voxel indices are
+// unique within a cell), and writes the window back in ascending order.  Cells larger than the window fall
+// back to an in-place bitonic sort in global memory.
+__global__ void __launch_bounds__(256) bp_bwd_order_kernel(const BwdParams p, const int bins_per_task) {
+  __shared__ int4 s_ent[8][kOrderWindow];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  int4* win = s_ent[wib];
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t ntasks = (p.M + kOrderBinsPerTask - 1) / kOrderBinsPerTask;
+  const int64_t ntasks = (p.M + bins_per_task - 1) / bins_per_task;
   for (int64_t task = warp_global; task < ntasks; task += nwarps) {
-    int64_t bin = task * kOrderBinsPerTask;
-    const int64_t bin_hi = min(p.M, bin + kOrderBinsPerTask);
+    int64_t bin = task * bins_per_task;
+    const int64_t bin_hi = min(p.M, bin + bins_per_task);
     while (bin < bin_hi) {
-      // lane l looks at cell bin+l
-      const int64_t mb = bin + lane;
+      const int64_t mb = bin + lane;  // lane l looks at cell bin+l
       const bool have = mb < bin_hi;
       const int sb = have ? __ldg(p.bin_start + mb) : 0x7fffffff;
       const int eb = have ? __ldg(p.bin_start + mb + 1) : 0x7fffffff;
       const int s0 = __shfl_sync(kFullB, sb, 0);
-      // whole cells that fit into a 32-entry window starting at s0 (eb is monotone -> leading run of trues)
-      const unsigned fits = __ballot_sync(kFullB, have && (eb - s0) <= 32);
-      const int nb = __popc(fits);  // leading run because monotone
-      if (nb == 0) {
-        // first cell has more than 32 entries
+      // whole cells that fit into the window starting at s0 (eb is monotone -> leading run of trues)
+      const unsigned fits = __ballot_sync(kFullB, have && (eb - s0) <= kOrderWindow);
+      const int nb = __popc(fits);
+      if (nb == 0) {  // first cell alone exceeds the window
         const int e0 = __shfl_sync(kFullB, eb, 0);
         bitonic_cell(reinterpret_cast<volatile int4*>(p.entries + s0), e0 - s0, lane);
         bin += 1;
@@ -268,25 +274,28 @@ __global__ void __launch_bounds__(256) bp_bwd_order_kernel(const BwdParams p, co
       }
       const int e_end = __shfl_sync(kFullB, eb, nb - 1);
       const int total = e_end - s0;
-      const unsigned need = __ballot_sync(kFullB, have && lane < nb && (eb - sb) >= 2);
+      const unsigned need = __ballot_sync(kFullB, lane < nb && (eb - sb) >= 2);
       if (need != 0u) {
-        const int pos = s0 + lane;
-        const bool on = lane < total;
-        int4 e = make_int4(0x7fffffff, 0, 0, 0);
-        if (on) e = p.entries[pos];
-        int ms = -1;  // start of my cell
-        for (int l = 0; l < nb; ++l) {
-          const int v = __shfl_sync(kFullB, sb, l);
-          if (v <= pos) ms = v;
-        }
-        int rank = 0;
-        for (int j = 0; j < total; ++j) {
-          const int nj = __shfl_sync(kFullB, e.x, j);
-          const int mj = __shfl_sync(kFullB, ms, j);
-          rank += (mj == ms && nj < e.x) ? 1 : 0;
+        for (int i = lane; i < total; i += 32) win[i] = p.entries[s0 + i];
+        __syncwarp();
+        for (int i0 = 0; i0 < total; i0 += 32) {
+          const int i = i0 + lane;
+          const bool on = i < total;
+          const int pos = s0 + i;
+          // my cell: the last of the nb cells whose start is <= pos (empty cells share their successor's start)
+          int ms = s0, me = s0;
+          for (int l = 0; l < nb; ++l) {
+            const int vs_ = __shfl_sync(kFullB, sb, l), ve = __shfl_sync(kFullB, eb, l);
+            if (on && vs_ <= pos && pos < ve) { ms = vs_; me = ve; }
+          }
+          if (on && me - ms >= 2) {
+            const int4 e = win[i];
+            int rank = 0;
+            for (int j = ms - s0; j < me - s0; ++j) rank += (win[j].x < e.x) ? 1 : 0;
+            p.entries[ms + rank] = e;
+          }
         }
         __syncwarp();
-        if (on) p.entries[ms + rank] = e;
       }
       bin += nb;
     }

@@ -182,3 +182,20 @@ def test_backward_without_forward_count_recomputes_it():
     assert torch.equal(g1, g2)
     assert torch.equal(g1.permute(0, 1, 4, 2, 3), g3)
     assert torch.equal(voxel.feats_to_nchw(g1), g3)
+
+
+def test_heavy_collisions_large_cells():
+    """Thousands of voxels landing in the same bilinear cell: exercises the >32-entry shared-memory rank sort and
+    the >256-entry in-place bitonic path of the `order` kernel (duplicated coords are legal inputs)."""
+    rng = np.random.default_rng(8)
+    inp = cases.bp_level(2, 2000, np.int64)
+    hot = inp["coords"][rng.choice(2000, 6, replace=False)]
+    reps = [hot[0:1].repeat(40, 0), hot[1:2].repeat(300, 0), hot[2:3].repeat(1500, 0), hot[3:6].repeat(90, 0)]
+    coords = np.concatenate([inp["coords"]] + reps, 0)
+    coords = coords[rng.permutation(coords.shape[0])]
+    inp["coords"] = np.ascontiguousarray(coords)
+    inp["grad_out"] = rng.standard_normal((coords.shape[0], 25), dtype=np.float32)
+    vol, cnt, g = run_cuda(inp)
+    check_vs_oracle("collisions", inp, vol, cnt, g)
+    _, _, g2 = run_cuda(inp)
+    np.testing.assert_array_equal(g, g2)
