@@ -15,8 +15,9 @@ SYMBOLS = (
     "d3m_kernel_launches", "d3m_profile_begin", "d3m_profile_end",
     "d3m_feats_nchw_to_nhwc", "d3m_feats_nhwc_to_nchw",
     "d3m_back_project_fwd_workspace", "d3m_back_project_fwd",
+    "d3m_back_project_fwd_partial", "d3m_back_project_fwd_finish",
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
-    "d3m_tsdf_create", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_integrate_host",
+    "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_integrate_host",
     "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches",
 )
 
@@ -55,12 +56,18 @@ def lib():
     L.d3m_back_project_fwd_workspace.restype = sz
     L.d3m_back_project_fwd.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd.restype = i32
+    L.d3m_back_project_fwd_partial.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.d3m_back_project_fwd_partial.restype = i32
+    L.d3m_back_project_fwd_finish.argtypes = [i64, i32, i32, vp, vp, vp, sz, vp]
+    L.d3m_back_project_fwd_finish.restype = i32
     L.d3m_back_project_bwd_workspace.argtypes = [i64, i32, i32, i32, i32, i32]
     L.d3m_back_project_bwd_workspace.restype = sz
     L.d3m_back_project_bwd.argtypes = [vp, i32, i64, vp, i32, f32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, sz, vp]
     L.d3m_back_project_bwd.restype = i32
     L.d3m_tsdf_create.argtypes = [i32, i32, i32, vp, f32, f32, i32, ctypes.POINTER(vp)]
     L.d3m_tsdf_create.restype = i32
+    L.d3m_tsdf_create_slab.argtypes = [i32, i32, i32, i32, vp, f32, f32, i32, ctypes.POINTER(vp)]
+    L.d3m_tsdf_create_slab.restype = i32
     L.d3m_tsdf_destroy.argtypes = [vp]
     L.d3m_tsdf_destroy.restype = i32
     L.d3m_tsdf_reset.argtypes = [vp, vp]

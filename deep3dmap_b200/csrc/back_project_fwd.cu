@@ -329,7 +329,23 @@ struct StatsParams {
   double* partial;  // (nchunks, B, 3)
   float* stats;     // (B, 2): mean, sd
   unsigned int* counter;
+  double* sums;     // (B, 3) Sz, Sz2, n+ of this call's voxels, or NULL (voxel-range sharding: all-reduced by the caller)
+  int finalize;     // 1: derive stats from this call's sums alone (unsharded)
 };
+
+// mean / sd of back_project.py:77-78 from the three fp64 sums
+__device__ __forceinline__ void stats_from_sums(double s, double s2, double c, float& mean, float& sd) {
+  if (c > 0.0) {
+    mean = (float)(s / c);
+    const double m = (double)mean;
+    double ssq = s2 - 2.0 * m * s + c * m * m;
+    if (ssq < 0.0) ssq = 0.0;
+    sd = __fadd_rn((float)sqrt(ssq), 1e-5f);
+  } else {
+    mean = __int_as_float(0x7fc00000);  // mean of an empty set is NaN in the reference; never used (z<=0 -> 0)
+    sd = 1e-5f;
+  }
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -386,20 +402,24 @@ __global__ void __launch_bounds__(kStatsThreads) bp_stats_kernel(const StatsPara
       const volatile double* q = p.partial + ((size_t)k * p.B + b) * 3;
       s += q[0]; s2 += q[1]; c += q[2];
     }
-    float mean, sd;
-    if (c > 0.0) {
-      mean = (float)(s / c);
-      const double m = (double)mean;
-      double ssq = s2 - 2.0 * m * s + c * m * m;
-      if (ssq < 0.0) ssq = 0.0;
-      sd = __fadd_rn((float)sqrt(ssq), 1e-5f);
-    } else {
-      mean = __int_as_float(0x7fc00000);  // mean of an empty set is NaN in the reference; never used (z<=0 -> 0)
-      sd = 1e-5f;
+    if (p.sums) { p.sums[3 * b] = s; p.sums[3 * b + 1] = s2; p.sums[3 * b + 2] = c; }
+    if (p.finalize) {
+      float mean, sd;
+      stats_from_sums(s, s2, c, mean, sd);
+      p.stats[2 * b] = mean;
+      p.stats[2 * b + 1] = sd;
     }
-    p.stats[2 * b] = mean;
-    p.stats[2 * b + 1] = sd;
   }
+}
+
+// voxel-range sharding: stats from the all-reduced sums of every shard
+__global__ void bp_stats_from_sums_kernel(const double* __restrict__ sums, float* __restrict__ stats, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  float mean, sd;
+  stats_from_sums(sums[3 * b], sums[3 * b + 1], sums[3 * b + 2], mean, sd);
+  stats[2 * b] = mean;
+  stats[2 * b + 1] = sd;
 }
 
 __global__ void __launch_bounds__(256) bp_normalise_kernel(const float* __restrict__ zbar, const int* __restrict__ bidx,
@@ -517,11 +537,9 @@ extern "C" size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C)
   return fwd_ws_layout(N, B).total;
 }
 
-extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
-                                    float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                                    const float* KRcam, float* out, float* count, void* workspace,
-                                    size_t workspace_bytes, void* stream_) {
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+static int fwd_check(const void* coords, int coords_kind, int64_t N, const float* origin, int B, const float* feats_nhwc,
+                     int V, int C, int H, int W, const float* KRcam, float* out, float* count, void* workspace,
+                     size_t workspace_bytes) {
   D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "back_project: no CUDA device (there is no CPU fallback)");
   D3M_REQUIRE(N >= 0 && B >= 1 && V >= 1 && C >= 1 && H >= 2 && W >= 2, D3M_ERR_ARG,
               "back_project: bad sizes N=%lld B=%d V=%d C=%d H=%d W=%d", (long long)N, B, V, C, H, W);
@@ -536,6 +554,31 @@ extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t
   const FwdWs w = fwd_ws_layout(N, B);
   D3M_REQUIRE(workspace_bytes >= w.total, D3M_ERR_WORKSPACE, "back_project: workspace %zu < %zu", workspace_bytes,
               w.total);
+  return D3M_OK;
+}
+
+static int fwd_normalise(int64_t N, int C, const FwdWs& w, unsigned char* ws, float* out, cudaStream_t stream) {
+  LaunchScope ls("bp_fwd_normalise", stream);
+  bp_normalise_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(
+      reinterpret_cast<const float*>(ws + w.zbar), reinterpret_cast<const int*>(ws + w.bidx),
+      reinterpret_cast<const float*>(ws + w.stats), out, N, C + 1);
+  D3M_CUDA_CHECK(cudaGetLastError());
+  return D3M_OK;
+}
+
+// gather + per-fragment depth sums; `depth_sums` != NULL -> sharded mode: sums are handed to the caller and the depth
+// channel is left un-normalised until d3m_back_project_fwd_finish.
+static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float* origin, int B, float voxel_size,
+                    const float* feats_nhwc, int V, int C, int H, int W, const float* KRcam, float* out, float* count,
+                    void* workspace, size_t workspace_bytes, double* depth_sums, cudaStream_t stream) {
+  int rc = fwd_check(coords, coords_kind, N, origin, B, feats_nhwc, V, C, H, W, KRcam, out, count, workspace,
+                     workspace_bytes);
+  if (rc != D3M_OK) return rc;
+  if (N == 0) {
+    if (depth_sums) D3M_CUDA_CHECK(cudaMemsetAsync(depth_sums, 0, sizeof(double) * 3 * (size_t)B, stream));
+    return D3M_OK;
+  }
+  const FwdWs w = fwd_ws_layout(N, B);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   FwdParams p;
   p.coords = coords; p.N = N; p.origin = origin; p.B = B; p.vs = voxel_size;
@@ -544,7 +587,6 @@ extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t
   p.zbar = reinterpret_cast<float*>(ws + w.zbar);
   p.bidx = reinterpret_cast<int*>(ws + w.bidx);
   p.counter = reinterpret_cast<unsigned int*>(ws + w.counter);
-  int rc;
   if (coords_kind == D3M_COORDS_F32) rc = launch_fwd<D3M_COORDS_F32>(p, stream);
   else if (coords_kind == D3M_COORDS_I64) rc = launch_fwd<D3M_COORDS_I64>(p, stream);
   else rc = launch_fwd<D3M_COORDS_I32>(p, stream);
@@ -554,15 +596,49 @@ extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t
   sp.partial = reinterpret_cast<double*>(ws + w.partial);
   sp.stats = reinterpret_cast<float*>(ws + w.stats);
   sp.counter = p.counter;
+  sp.sums = depth_sums;
+  sp.finalize = depth_sums ? 0 : 1;
   {
     LaunchScope ls("bp_fwd_stats", stream);
     bp_stats_kernel<<<w.nchunks, kStatsThreads, 0, stream>>>(sp);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
+  if (depth_sums) return D3M_OK;
+  return fwd_normalise(N, C, w, ws, out, stream);
+}
+
+extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                    float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
+                                    const float* KRcam, float* out, float* count, void* workspace,
+                                    size_t workspace_bytes, void* stream_) {
+  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats_nhwc, V, C, H, W, KRcam, out, count, workspace,
+                  workspace_bytes, nullptr, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int d3m_back_project_fwd_partial(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                            float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
+                                            const float* KRcam, float* out, float* count, double* depth_sums,
+                                            void* workspace, size_t workspace_bytes, void* stream_) {
+  D3M_REQUIRE(depth_sums, D3M_ERR_ARG, "back_project_fwd_partial: NULL depth_sums");
+  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats_nhwc, V, C, H, W, KRcam, out, count, workspace,
+                  workspace_bytes, depth_sums, static_cast<cudaStream_t>(stream_));
+}
+
+extern "C" int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sums, float* out,
+                                           void* workspace, size_t workspace_bytes, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "back_project: no CUDA device (there is no CPU fallback)");
+  D3M_REQUIRE(N >= 0 && B >= 1 && C >= 1, D3M_ERR_ARG, "back_project_fwd_finish: bad sizes");
+  if (N == 0) return D3M_OK;
+  D3M_REQUIRE(depth_sums && out && workspace, D3M_ERR_ARG, "back_project_fwd_finish: NULL pointer");
+  const FwdWs w = fwd_ws_layout(N, B);
+  D3M_REQUIRE(workspace_bytes >= w.total, D3M_ERR_WORKSPACE, "back_project_fwd_finish: workspace %zu < %zu",
+              workspace_bytes, w.total);
+  unsigned char* ws = static_cast<unsigned char*>(workspace);
   {
-    LaunchScope ls("bp_fwd_normalise", stream);
-    bp_normalise_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(p.zbar, p.bidx, sp.stats, out, N, C + 1);
+    LaunchScope ls("bp_fwd_stats_from_sums", stream);
+    bp_stats_from_sums_kernel<<<(B + 127) / 128, 128, 0, stream>>>(depth_sums, reinterpret_cast<float*>(ws + w.stats), B);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
-  return D3M_OK;
+  return fwd_normalise(N, C, w, ws, out, stream);
 }

@@ -47,6 +47,7 @@ struct TsdfParams {
   float* weight;
   float* color;
   int dx, dy, dz;
+  int xoff;             // global x index of local plane 0 (slab sharding), 0 otherwise
   float ox, oy, oz, vs, trunc;
   const Frame* frames;
   int F;
@@ -97,7 +98,7 @@ __device__ __forceinline__ bool frame_tile_box(const TsdfParams& p, const Frame&
       mn[a] = fminf(mn[a], q);
       mx[a] = fmaxf(mx[a], q);
     }
-  const float org[3] = {p.ox, p.oy, p.oz};
+  const float org[3] = {p.ox + (float)p.xoff * p.vs, p.oy, p.oz};  // cull geometry only (conservative)
   const int dims[3] = {p.dx, p.dy, p.dz};
   const int tdim[3] = {kTileX, kTileY, kTileZ};
 #pragma unroll
@@ -231,7 +232,8 @@ __global__ void __launch_bounds__(kTsdfThreads) tsdf_integrate_kernel(const Tsdf
     // tile box over voxel CENTRES, world space
     const int x0 = tx * kTileX, y0 = ty * kTileY, z0 = tz * kTileZ;
     const int x1 = min(p.dx, x0 + kTileX) - 1, y1 = min(p.dy, y0 + kTileY) - 1, z1 = min(p.dz, z0 + kTileZ) - 1;
-    const float c[3] = {p.ox + 0.5f * (x0 + x1) * p.vs, p.oy + 0.5f * (y0 + y1) * p.vs, p.oz + 0.5f * (z0 + z1) * p.vs};
+    const float c[3] = {p.ox + (0.5f * (x0 + x1) + (float)p.xoff) * p.vs, p.oy + 0.5f * (y0 + y1) * p.vs,
+                        p.oz + 0.5f * (z0 + z1) * p.vs};
     const float h[3] = {0.5f * (x1 - x0) * p.vs, 0.5f * (y1 - y0) * p.vs, 0.5f * (z1 - z0) * p.vs};
     // ---- ordered list of frames that can touch this tile --------------------------------------
     if (tid == 0) s_n = 0;
@@ -283,7 +285,7 @@ __global__ void __launch_bounds__(kTsdfThreads) tsdf_integrate_kernel(const Tsdf
 #pragma unroll
       for (int i = 0; i < kVoxPerThread; ++i) {
         if (inb[i])
-          integrate_voxel<SEM, COLOR>(p, fr, depth, cimg, (float)(x0 + lxg * kVoxPerThread + i), (float)y, (float)z,
+          integrate_voxel<SEM, COLOR>(p, fr, depth, cimg, (float)(p.xoff + x0 + lxg * kVoxPerThread + i), (float)y, (float)z,
                                       tv[i], wv[i], cv[i], dirty[i]);
       }
     }
@@ -307,7 +309,7 @@ __global__ void fill_kernel(float* p, float v, int64_t n) {
 using namespace d3m;
 
 struct d3m_tsdf {
-  int dx, dy, dz, device, sms;
+  int dx, dy, dz, xoff, device, sms;
   float origin[3], vs, trunc;
   float *tsdf, *weight, *color;
   size_t nvox;
@@ -398,7 +400,7 @@ static int tsdf_launch(d3m_tsdf* h, const float* depth, const float* cimg, int F
                        int flags, cudaStream_t stream) {
   TsdfParams p;
   p.tsdf = h->tsdf; p.weight = h->weight; p.color = h->color;
-  p.dx = h->dx; p.dy = h->dy; p.dz = h->dz;
+  p.dx = h->dx; p.dy = h->dy; p.dz = h->dz; p.xoff = h->xoff;
   p.ox = h->origin[0]; p.oy = h->origin[1]; p.oz = h->origin[2];
   p.vs = h->vs; p.trunc = h->trunc;
   p.frames = d_frames; p.F = F; p.depth = depth; p.cimg = cimg; p.H = H; p.W = W;
@@ -443,16 +445,22 @@ static int ensure_frames(d3m_tsdf* h, int F) {
 
 extern "C" int d3m_tsdf_create(int dim_x, int dim_y, int dim_z, const float* origin3_host, float voxel_size,
                                float trunc_margin, int device, d3m_tsdf** out_handle) {
+  return d3m_tsdf_create_slab(dim_x, dim_y, dim_z, 0, origin3_host, voxel_size, trunc_margin, device, out_handle);
+}
+
+extern "C" int d3m_tsdf_create_slab(int dim_x, int dim_y, int dim_z, int x_begin, const float* origin3_host,
+                                    float voxel_size, float trunc_margin, int device, d3m_tsdf** out_handle) {
   D3M_REQUIRE(out_handle, D3M_ERR_ARG, "tsdf_create: NULL out_handle");
   *out_handle = nullptr;
   D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "tsdf_create: no CUDA device (there is no CPU fallback)");
-  D3M_REQUIRE(dim_x > 0 && dim_y > 0 && dim_z > 0 && origin3_host && voxel_size > 0.f && trunc_margin > 0.f,
+  D3M_REQUIRE(dim_x > 0 && dim_y > 0 && dim_z > 0 && x_begin >= 0 && origin3_host && voxel_size > 0.f &&
+                  trunc_margin > 0.f,
               D3M_ERR_ARG, "tsdf_create: bad arguments");
   D3M_CUDA_CHECK(cudaSetDevice(device));
   d3m_tsdf* h = new (std::nothrow) d3m_tsdf();
   D3M_REQUIRE(h, D3M_ERR_ARG, "tsdf_create: out of host memory");
   memset(h, 0, sizeof(*h));
-  h->dx = dim_x; h->dy = dim_y; h->dz = dim_z; h->device = device;
+  h->dx = dim_x; h->dy = dim_y; h->dz = dim_z; h->xoff = x_begin; h->device = device;
   h->vs = voxel_size; h->trunc = trunc_margin;
   memcpy(h->origin, origin3_host, 12);
   h->nvox = (size_t)dim_x * dim_y * dim_z;

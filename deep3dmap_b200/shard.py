@@ -1,0 +1,192 @@
+"""Multi-GPU partitioning of the lifting hot path: one process per GPU, `torch.distributed` (NCCL over NVLink on
+the box, gloo in the CPU tests) for the few exchange steps the path really has.
+
+  * fragment-parallel (BASELINE config 4) -- the reference's own data-parallel axis (`back_project.py:28` loops
+    the fragments, DDP runs `samples_per_gpu=1`): `fragments_of_rank` deals fragments round-robin; there is NO
+    data-path collective, forward or backward.
+  * voxel-range sharding (BASELINE config 5) -- `voxel_range` splits the (sorted) coordinate list into
+    `world_size` contiguous slices; feats and KRcam are replicated.  `back_project_voxel_sharded` then needs
+      (1) one all-reduce of 3 fp64 scalars per fragment for the depth normalisation (`back_project.py:77-80`),
+      (2) in backward, one all-reduce(sum) of grad_feats (every rank holds the partial sums of its voxels), and
+      (3) `all_gather_rows` of the per-shard count / occupancy (or full rows) only where the next coarse-to-fine
+          level needs the complete set (`neucon_network.py:132, 180-196`).
+    Collectives are issued in a fixed order, so results are deterministic run to run.
+  * TSDF x-slab sharding -- `tsdf_slab` gives each rank a contiguous range of x planes; integration needs no
+    exchange at all; `TSDFVolume(..., slab=(x_begin, x_end))` + `gather_tsdf_volume` reassemble the volume.
+
+Nothing here computes on the CPU: the per-rank work is the CUDA path of `voxel.py` / `tsdf.py`.  The gloo tests
+exercise the partition / collective logic with a test double for the local kernels (`local_ops=`).
+"""
+import torch
+import torch.distributed as dist
+
+from . import _lib, voxel
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# partitions (pure index arithmetic, identical on every rank)
+# ---------------------------------------------------------------------------------------------------------------
+def _world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def fragments_of_rank(n_fragments, rank=None, world_size=None, group=None):
+    """Round-robin deal of fragment ids: rank r owns r, r+W, r+2W, ...."""
+    if rank is None or world_size is None:
+        rank, world_size = _world(group)
+    return list(range(rank, n_fragments, world_size))
+
+
+def voxel_range(n_voxels, rank=None, world_size=None, group=None):
+    """[begin, end) of this rank's contiguous slice of an N-row coordinate list; sizes differ by at most 1 and
+    the slices of ranks 0..W-1 concatenate to the full list in order."""
+    if rank is None or world_size is None:
+        rank, world_size = _world(group)
+    q, r = divmod(int(n_voxels), int(world_size))
+    begin = rank * q + min(rank, r)
+    return begin, begin + q + (1 if rank < r else 0)
+
+
+def tsdf_slab(dim_x, rank=None, world_size=None, group=None, align=8):
+    """[x_begin, x_end) planes of this rank; boundaries are multiples of `align` (the kernel's x tile) so that no
+    tile straddles two ranks."""
+    if rank is None or world_size is None:
+        rank, world_size = _world(group)
+    tiles = (int(dim_x) + align - 1) // align
+    b, e = voxel_range(tiles, rank, world_size)
+    return min(b * align, dim_x), min(e * align, dim_x)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# collectives with variable shard sizes
+# ---------------------------------------------------------------------------------------------------------------
+def all_gather_rows(local, group=None, sizes=None):
+    """Concatenate the ranks' (n_r, ...) tensors along dim 0 in rank order.  One size exchange (skipped when
+    `sizes` is given, e.g. from `voxel_range`) + ONE padded `all_gather_into_tensor`."""
+    rank, world = _world(group)
+    if world == 1:
+        return local
+    local = local.contiguous()
+    if sizes is None:
+        n = torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device)
+        alln = torch.empty(world, dtype=torch.int64, device=local.device)
+        dist.all_gather_into_tensor(alln, n, group=group)
+        sizes = [int(x) for x in alln.tolist()]
+    nmax = max(sizes)
+    tail = tuple(local.shape[1:])
+    if local.shape[0] == nmax:
+        padded = local
+    else:
+        padded = local.new_zeros((nmax,) + tail)
+        padded[: local.shape[0]] = local
+    out = local.new_empty((world * nmax,) + tail)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    if all(s == nmax for s in sizes):
+        return out
+    return torch.cat([out[r * nmax: r * nmax + s] for r, s in enumerate(sizes)], 0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# voxel-range sharded back_project
+# ---------------------------------------------------------------------------------------------------------------
+class _CudaLocalOps:
+    """The per-rank kernels (libd3m.so).  Tests substitute an object with the same three methods."""
+
+    @staticmethod
+    def forward_partial(coords, origin, voxel_size, feats, KRcam):
+        """-> (out (n,C+1) with RAW mean depth in the last column, count (n,), depth_sums (B,3) float64, state)"""
+        L = _lib.lib()
+        if not feats.is_cuda:
+            raise _lib.D3MError("back_project_voxel_sharded: feats must live on a CUDA device (no CPU fallback)")
+        dev = feats.device
+        coords, origin, KRcam = voxel._prep_small(coords, origin, KRcam, dev)
+        nhwc = voxel.feats_to_channels_last(feats.float())
+        V, B, H, W, C = nhwc.shape
+        N = coords.shape[0]
+        out = torch.empty((N, C + 1), dtype=torch.float32, device=dev)
+        count = torch.empty((N,), dtype=torch.float32, device=dev)
+        sums = torch.zeros((B, 3), dtype=torch.float64, device=dev)
+        ws, ws_bytes = voxel._workspace("f", (max(N, 1), B, V, C), dev)
+        if N > 0:
+            with voxel._on_device(dev):
+                rc = L.d3m_back_project_fwd_partial(coords.data_ptr(), voxel._COORD_KIND[coords.dtype], N,
+                                                    origin.data_ptr(), B, float(voxel_size), nhwc.data_ptr(), V, C, H, W,
+                                                    KRcam.data_ptr(), out.data_ptr(), count.data_ptr(), sums.data_ptr(),
+                                                    ws.data_ptr(), ws_bytes, voxel._stream(dev))
+            _lib.check(rc, "d3m_back_project_fwd_partial")
+        return out, count, sums, (ws, ws_bytes, tuple(nhwc.shape), coords, origin, KRcam)
+
+    @staticmethod
+    def forward_finish(out, sums, state):
+        ws, ws_bytes, (V, B, H, W, C) = state[0], state[1], state[2]
+        N = out.shape[0]
+        if N == 0:
+            return out
+        dev = out.device
+        with voxel._on_device(dev):
+            rc = _lib.lib().d3m_back_project_fwd_finish(N, B, C, sums.data_ptr(), out.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                        voxel._stream(dev))
+        _lib.check(rc, "d3m_back_project_fwd_finish")
+        return out
+
+    @staticmethod
+    def backward(state, voxel_size, grad_out, count):
+        _, _, nhwc_shape, coords, origin, KRcam = state
+        return voxel.back_project_backward(coords, origin, voxel_size, nhwc_shape, KRcam, grad_out, nchw=True,
+                                           count=count)
+
+
+class _BackProjectVoxelSharded(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feats, coords_local, origin, voxel_size, KRcam, group, ops):
+        out, count, sums, state = ops.forward_partial(coords_local, origin, voxel_size, feats, KRcam)
+        if _world(group)[1] > 1:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)  # 3 fp64 scalars per fragment
+        out = ops.forward_finish(out, sums, state)
+        ctx.state, ctx.ops, ctx.group, ctx.voxel_size = state, ops, group, float(voxel_size)
+        ctx.save_for_backward(count)
+        ctx.mark_non_differentiable(count)
+        ctx.set_materialize_grads(False)
+        return out, count
+
+    @staticmethod
+    def backward(ctx, grad_vol, grad_count):
+        (count,) = ctx.saved_tensors
+        if not ctx.needs_input_grad[0]:
+            return (None,) * 7
+        if grad_vol is None:
+            # this rank's slice received no gradient, but the peers still wait in the all-reduce
+            grad_vol = torch.zeros((count.shape[0], ctx.state[2][4] + 1), dtype=torch.float32, device=count.device)
+        g = grad_vol if (grad_vol.is_contiguous() and grad_vol.dtype == torch.float32) else grad_vol.contiguous().float()
+        grad = ctx.ops.backward(ctx.state, ctx.voxel_size, g, count)
+        if _world(ctx.group)[1] > 1:
+            dist.all_reduce(grad, op=dist.ReduceOp.SUM, group=ctx.group)  # partial sums of every rank's voxels
+        return grad, None, None, None, None, None, None
+
+
+def back_project_voxel_sharded(coords_local, origin, voxel_size, feats, KRcam, group=None, local_ops=None):
+    """`back_project` on this rank's slice of the voxel list (`voxel_range`), feats / KRcam replicated.
+
+    Returns (volume_local (n_r, C+1), count_local (n_r,)) whose concatenation over ranks equals the single-GPU
+    `back_project` on the full list: features and count bit for bit, the depth channel up to the fp64 summation
+    order of the three normalisation scalars.  Backward all-reduces grad_feats, so every rank ends up with the full
+    gradient of its (replicated) feature maps."""
+    return _BackProjectVoxelSharded.apply(feats, coords_local, origin, voxel_size, KRcam, group,
+                                          local_ops or _CudaLocalOps)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# TSDF slabs
+# ---------------------------------------------------------------------------------------------------------------
+def gather_tsdf_volume(local_tsdf, local_weight, dim_x, group=None):
+    """Reassemble (tsdf, weight) of the full volume from the ranks' x slabs (device tensors (x_r, Y, Z))."""
+    rank, world = _world(group)
+    if world == 1:
+        return local_tsdf, local_weight
+    sizes = []
+    for r in range(world):
+        b, e = tsdf_slab(dim_x, r, world)
+        sizes.append(e - b)
+    return (all_gather_rows(local_tsdf, group, sizes), all_gather_rows(local_weight, group, sizes))

@@ -41,13 +41,13 @@ class _DeviceArray:
 class _Handle:
     """RAII wrapper of `d3m_tsdf*`."""
 
-    def __init__(self, dims, origin, voxel_size, trunc, device):
+    def __init__(self, dims, origin, voxel_size, trunc, device, x_begin=0):
         _lib.require_device()
         self.ptr = ctypes.c_void_p()
         org = np.ascontiguousarray(origin, dtype=np.float32)
-        rc = _lib.lib().d3m_tsdf_create(int(dims[0]), int(dims[1]), int(dims[2]), _f32p(org), float(voxel_size),
-                                        float(trunc), int(device), ctypes.byref(self.ptr))
-        _lib.check(rc, "d3m_tsdf_create")
+        rc = _lib.lib().d3m_tsdf_create_slab(int(dims[0]), int(dims[1]), int(dims[2]), int(x_begin), _f32p(org),
+                                             float(voxel_size), float(trunc), int(device), ctypes.byref(self.ptr))
+        _lib.check(rc, "d3m_tsdf_create_slab")
         self.dims = tuple(int(d) for d in dims)
 
     def close(self):
@@ -92,10 +92,14 @@ class TSDFVolume:
       * colour: like the reference GPU kernel (unconditional `return` at :129) the colour volume stays 0
         unless `integrate_color=True` is passed, which runs the running average of :130-141;
       * voxel index decomposition is integer (the reference's float one, :89-91, breaks above 2^24 voxels);
-      * `integrate_batch` (many frames, one launch) is an extension.
+      * `integrate_batch` (many frames, one launch) is an extension;
+      * `slab=(x_begin, x_end)` (extension, multi-GPU): this object owns only those x planes of the volume described
+        by `vol_bnds`; `get_volume()` then returns arrays of shape (x_end-x_begin, Y, Z) that are bit-identical to
+        the same planes of the unsharded volume (see `shard.tsdf_slab` / `shard.gather_tsdf_volume`).
     """
 
-    def __init__(self, vol_bnds, voxel_size, use_gpu=True, margin=5, device=0, integrate_color=False, stream=None):
+    def __init__(self, vol_bnds, voxel_size, use_gpu=True, margin=5, device=0, integrate_color=False, stream=None,
+                 slab=None):
         vol_bnds = np.asarray(vol_bnds)
         assert vol_bnds.shape == (3, 2), "[!] `vol_bnds` should be of shape (3, 2)."
         if not use_gpu:
@@ -113,8 +117,12 @@ class TSDFVolume:
         self.gpu_mode = 1
         self._integrate_color = bool(integrate_color)
         self._stream = stream
-        self._h = _Handle(self._vol_dim, self._vol_origin, np.float32(self._voxel_size), np.float32(self._trunc_margin),
-                          device)
+        self._slab = (0, int(self._vol_dim[0])) if slab is None else (int(slab[0]), int(slab[1]))
+        if not (0 <= self._slab[0] < self._slab[1] <= int(self._vol_dim[0])):
+            raise ValueError("slab must satisfy 0 <= x_begin < x_end <= %d" % int(self._vol_dim[0]))
+        self._local_dim = np.array([self._slab[1] - self._slab[0], self._vol_dim[1], self._vol_dim[2]], dtype=int)
+        self._h = _Handle(self._local_dim, self._vol_origin, np.float32(self._voxel_size),
+                          np.float32(self._trunc_margin), device, x_begin=self._slab[0])
         self._tsdf_vol_cpu = None
         self._weight_vol_cpu = None
         self._color_vol_cpu = None
@@ -182,11 +190,12 @@ class TSDFVolume:
 
     # -- results ----------------------------------------------------------------------------------
     def get_volume(self):
-        """(tsdf, color, weight) float32 numpy arrays of shape `_vol_dim` (tsdf_volume.py:302-307)."""
+        """(tsdf, color, weight) float32 numpy arrays of shape `_vol_dim` (tsdf_volume.py:302-307); with `slab=`
+        only this rank's x planes."""
         if self._tsdf_vol_cpu is None:
-            self._tsdf_vol_cpu = np.empty(self._vol_dim, dtype=np.float32)
-            self._weight_vol_cpu = np.empty(self._vol_dim, dtype=np.float32)
-            self._color_vol_cpu = np.empty(self._vol_dim, dtype=np.float32)
+            self._tsdf_vol_cpu = np.empty(self._local_dim, dtype=np.float32)
+            self._weight_vol_cpu = np.empty(self._local_dim, dtype=np.float32)
+            self._color_vol_cpu = np.empty(self._local_dim, dtype=np.float32)
         rc = _lib.lib().d3m_tsdf_download(self._h.ptr, _f32p(self._tsdf_vol_cpu), _f32p(self._weight_vol_cpu),
                                           _f32p(self._color_vol_cpu), self._stream)
         _lib.check(rc, "d3m_tsdf_download")

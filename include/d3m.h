@@ -82,6 +82,21 @@ int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const f
                          const float* KRcam, float* out, float* count, void* workspace,
                          size_t workspace_bytes, void* stream);
 
+/* Voxel-range sharding (BASELINE config 5): every rank runs the gather on its contiguous slice of the coordinate
+ * list; the only cross-voxel coupling of the reference, the per-fragment depth normalisation
+ * (back_project.py:77-80), is split in two so that the caller can all-reduce three fp64 scalars per fragment
+ * in between:
+ *   _partial  as d3m_back_project_fwd, but leaves the RAW mean depth in out[:,C] and writes this slice's
+ *             (sum z, sum z^2, #{z>0}) per fragment to depth_sums (B,3) float64 on the device;
+ *   _finish   takes the (all-reduced) sums, derives mean / L2-norm and normalises out[:,C] in place.  `workspace`
+ *             must be the buffer handed to _partial for the same slice, untouched in between. */
+int d3m_back_project_fwd_partial(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                 float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
+                                 const float* KRcam, float* out, float* count, double* depth_sums,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sums, float* out, void* workspace,
+                                size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * back_project backward w.r.t. feats  (replaces autograd through back_project.py:55-73:
  * div backward, mask, grid_sampler_2d_backward).  Deterministic: samples are binned per texel with
@@ -118,6 +133,11 @@ enum {
 
 int d3m_tsdf_create(int dim_x, int dim_y, int dim_z, const float* origin3_host, float voxel_size,
                     float trunc_margin, int device, d3m_tsdf** out_handle);
+/* x-slab of a larger volume (multi-GPU slab sharding): the handle owns planes [x_begin, x_begin+dim_x_local) of a
+ * volume whose voxel (0,0,0) sits at origin3_host; world positions are computed from the GLOBAL voxel index, so
+ * the slabs of all ranks concatenated along x are bit-identical to the unsharded volume. */
+int d3m_tsdf_create_slab(int dim_x_local, int dim_y, int dim_z, int x_begin, const float* origin3_host,
+                         float voxel_size, float trunc_margin, int device, d3m_tsdf** out_handle);
 int d3m_tsdf_destroy(d3m_tsdf* h);
 int d3m_tsdf_reset(d3m_tsdf* h, void* stream);
 

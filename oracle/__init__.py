@@ -82,8 +82,10 @@ def _prep(coords, origin, feats_shape, KRcam):
     return coords, origin, KRcam
 
 
-def back_project_fwd(coords, origin, voxel_size, feats, KRcam, interp="fma"):
-    """Oracle of `back_project` forward.  Returns (volume (N,C+1) f32, count (N,) f32)."""
+def back_project_fwd(coords, origin, voxel_size, feats, KRcam, interp="fma", raw_depth=False):
+    """Oracle of `back_project` forward.  Returns (volume (N,C+1) f32, count (N,) f32).
+    raw_depth=True stops before the per-fragment normalisation (`back_project.py:77-80`): the last column then
+    holds the plain mean depth of :76."""
     feats = np.ascontiguousarray(feats, dtype=np.float32)
     V, B, C, H, W = feats.shape
     coords, origin, KRcam = _prep(coords, origin, feats.shape, KRcam)
@@ -92,7 +94,7 @@ def back_project_fwd(coords, origin, voxel_size, feats, KRcam, interp="fma"):
     cnt = np.zeros((N,), dtype=np.float32)
     rc = lib().orc_back_project_fwd(_p(coords), COORD_KIND[coords.dtype], N, _p(origin), B,
                                     np.float32(voxel_size), _p(feats), V, C, H, W, _p(KRcam),
-                                    _p(out), _p(cnt), INTERP[interp])
+                                    _p(out), _p(cnt), INTERP[interp] | (0x100 if raw_depth else 0))
     if rc != 0:
         raise RuntimeError("oracle fwd failed")
     return out, cnt

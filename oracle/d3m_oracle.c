@@ -26,6 +26,9 @@ enum { ORC_COORDS_F32 = 0, ORC_COORDS_I64 = 1, ORC_COORDS_I32 = 2 };
 /* bilinear-sum flavour: 0 = aten CPU kernel (separate mul/add, GridSamplerKernel.cpp),
  *                       1 = aten CUDA kernel (out_acc += val*w contracted to FMA, GridSampler.cu) */
 enum { ORC_INTERP_MULADD = 0, ORC_INTERP_FMA = 1 };
+/* OR-ed into interp_mode: leave the raw mean depth (back_project.py:76) in out[:,C], i.e. stop before the
+ * per-fragment normalisation of :77-80 (used by the voxel-range sharding tests, which all-reduce its sums) */
+enum { ORC_RAW_DEPTH = 0x100 };
 
 int orc_num_threads(void) {
 #ifdef _OPENMP
@@ -118,6 +121,8 @@ int orc_back_project_fwd(const void* coords, int ckind, int64_t N, const float* 
                          const float* feats, int V, int C, int H, int W, const float* KR,
                          float* out, float* count, int interp_mode) {
   const int64_t HW = (int64_t)H * W;
+  const int raw_depth = (interp_mode & ORC_RAW_DEPTH) != 0;
+  interp_mode &= 0xff;
   memset(out, 0, sizeof(float) * (size_t)N * (C + 1));
   memset(count, 0, sizeof(float) * (size_t)N);
   int* batch_of = (int*)malloc(sizeof(int) * (size_t)(N > 0 ? N : 1));
@@ -177,7 +182,7 @@ int orc_back_project_fwd(const void* coords, int ckind, int64_t N, const float* 
     free(acc);
   }
   /* per-batch depth normalisation, back_project.py:77-80 */
-  for (int b = 0; b < B; ++b) {
+  for (int b = 0; b < B && !raw_depth; ++b) {
     double sum = 0.0; int64_t np_ = 0;
     for (int64_t n = 0; n < N; ++n)
       if (batch_of[n] == b && out[n * (C + 1) + C] > 0.0f) { sum += (double)out[n * (C + 1) + C]; ++np_; }
