@@ -54,15 +54,15 @@ def lib():
         f.restype = i32
     L.d3m_back_project_fwd_workspace.argtypes = [i64, i32, i32, i32]
     L.d3m_back_project_fwd_workspace.restype = sz
-    L.d3m_back_project_fwd.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, sz, vp]
+    L.d3m_back_project_fwd.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd.restype = i32
-    L.d3m_back_project_fwd_partial.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.d3m_back_project_fwd_partial.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd_partial.restype = i32
     L.d3m_back_project_fwd_finish.argtypes = [i64, i32, i32, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd_finish.restype = i32
     L.d3m_back_project_bwd_workspace.argtypes = [i64, i32, i32, i32, i32, i32]
     L.d3m_back_project_bwd_workspace.restype = sz
-    L.d3m_back_project_bwd.argtypes = [vp, i32, i64, vp, i32, f32, i32, i32, i32, i32, vp, vp, vp, vp, i32, vp, sz, vp]
+    L.d3m_back_project_bwd.argtypes = [vp, i32, i64, vp, i32, f32, i32, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, sz, vp]
     L.d3m_back_project_bwd.restype = i32
     L.d3m_tsdf_create.argtypes = [i32, i32, i32, vp, f32, f32, i32, ctypes.POINTER(vp)]
     L.d3m_tsdf_create.restype = i32

@@ -13,9 +13,12 @@
 //   fill    project again, claim a slot in the cell with an integer atomic, store {n, fx, fy} (16 B).
 //   order   sort every cell's entries by voxel index (windowed warp rank-sort; in-place bitonic for cells
 //           with more than 32 entries) -- this removes the only nondeterminism (slot claim order).
-//   gather  lane group per texel: walk the 4 neighbouring cells (as nw, ne, sw, se corner), per entry one
-//           128-bit broadcast load of the entry and R 128-bit loads of the ghat row per lane; plain fp32
-//           mul + add in entry order; one coalesced 128-bit store of the texel's gradient.
+//   gather  CTA per (TY x TX) tile of texels of one map: lane groups walk the (TY+1) x (TX+1) bilinear CELLS that
+//           touch the tile; every entry's ghat row is loaded ONCE (R 128-bit loads per lane) and feeds the four
+//           corner sums nw/ne/sw/se of its cell (fp32 mul + add in entry order).  The 4 per-cell partials go to
+//           shared memory; after one barrier every texel adds its four partials in the fixed order
+//           nw(y,x) + ne(y,x-1) + sw(y-1,x) + se(y-1,x-1) and is stored once.  (A texel-centric walk reads every
+//           row four times and was bound by L2->SM load latency.)
 #include "d3m_common.cuh"
 
 namespace d3m {
@@ -37,9 +40,11 @@ struct BwdParams {
   const float* grad_out;
   const float* count;  // (N,) view counts from the forward pass, or the workspace copy computed by bp_bwd_count_kernel
   float* ghat;
-  int* bin_cnt;
+  int* bin_cnt;          // per-cell histogram: workspace copy, or the one the forward pass produced (read-only then)
+  int* bin_cursor;       // per-cell next free entry position of the fill pass (scan initialises it to bin_start)
   int* bin_start;  // M+1
-  int4* entries;
+  int4* entries;         // {voxel, fx, fy, cell} in slot-claim order (fill)
+  int4* sorted;          // the same entries, every cell in ascending voxel order (order)
   float* grad_feats;
   int64_t M;  // V*B*H*W cells
   unsigned long long* scan_state;  // nchunks words, zeroed together with bin_cnt
@@ -49,7 +54,7 @@ struct BwdParams {
 };
 
 constexpr int kSampleThreads = 256;
-constexpr int kGhatPerThread = 4;
+constexpr int kGhatSteps = 4;       // row groups in flight per warp of the pre-division pass
 
 // Only used when the caller does not hand over the forward pass's `count`: valid views per voxel.
 template <int KIND>
@@ -73,39 +78,14 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_count_kernel(const BwdP
   cnt_out[n] = (float)cnt;
 }
 
-// One thread per (voxel, view) pair: blockIdx.y = view for y < V.  Short dependency chains and N*V-way
-// parallelism instead of a 9-deep serial loop per voxel (these passes are latency-bound at fragment size).
-//   FILL = false: histogram the valid samples per bilinear cell (integer RED); the extra grid rows y >= V
-//                 compute ghat[n,c] = grad_out[n,c] / max(count[n],1) (div backward of back_project.py:72),
-//                 re-packed to 16-byte aligned rows of C floats, one element per thread-iteration.
-//   FILL = true : claim a slot in the cell (integer atomic), store {n, fx, fy}.
+// One thread per (voxel, view) pair: blockIdx.y = view.  Short dependency chains and N*V-way parallelism instead of
+// a 9-deep serial loop per voxel (these passes are latency-bound at fragment size).
+//   FILL = false: histogram the valid samples per bilinear cell (integer RED).  Skipped entirely when the forward
+//                 pass already produced the histogram (d3m_back_project_fwd(..., cell_hist)).
+//   FILL = true : claim the cell's next entry position (one integer atomic on the cursor), store {n, fx, fy, cell}.
 template <int KIND, bool FILL>
 __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const BwdParams p) {
   const int v = blockIdx.y;
-  if (!FILL && v >= p.V) {
-    const int C = p.C, C1 = C + 1;
-    const int64_t total = p.N * C;
-    const int64_t blk = (int64_t)(v - p.V) * gridDim.x + blockIdx.x;
-    const int64_t base = blk * (kSampleThreads * kGhatPerThread) + threadIdx.x;
-    float g[kGhatPerThread], d[kGhatPerThread];
-#pragma unroll
-    for (int k = 0; k < kGhatPerThread; ++k) {  // all loads first
-      const int64_t i = base + (int64_t)k * kSampleThreads;
-      g[k] = 0.f; d[k] = 1.f;
-      if (i < total) {
-        const int64_t r = i / C;
-        const int c = (int)(i - r * C);
-        g[k] = __ldg(p.grad_out + r * C1 + c);
-        d[k] = fmaxf(__ldg(p.count + r), 1.0f);
-      }
-    }
-#pragma unroll
-    for (int k = 0; k < kGhatPerThread; ++k) {
-      const int64_t i = base + (int64_t)k * kSampleThreads;
-      if (i < total) p.ghat[i] = __fdiv_rn(g[k], d[k]);
-    }
-    return;
-  }
   const int64_t n = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
   if (n >= p.N) return;
   float cx, cy, cz;
@@ -122,9 +102,8 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const Bwd
   if (!FILL) {
     atomicAdd(p.bin_cnt + key, 1);
   } else {
-    const int slot = atomicSub(p.bin_cnt + key, 1) - 1;  // counts back to zero; order fixed later by `order`
-    const int pos = __ldg(p.bin_start + key) + slot;
-    p.entries[pos] = make_int4((int)n, __float_as_int(s.fx), __float_as_int(s.fy), 0);
+    const int pos = atomicAdd(p.bin_cursor + key, 1);  // claim order is arbitrary; `order` fixes it
+    p.entries[pos] = make_int4((int)n, __float_as_int(s.fx), __float_as_int(s.fy), key);
   }
 }
 
@@ -133,10 +112,57 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const Bwd
 // aggregate, walk back over predecessors until they meet an inclusive prefix, then publish their own.
 // state word = (flag << 32) | value, flag 0 = not ready, 1 = aggregate, 2 = inclusive prefix.  Integer sums:
 // the result does not depend on the order in which CTAs arrive.
-__global__ void __launch_bounds__(kScanThreads) bp_scan_kernel(const BwdParams p) {
+//
+// The same launch carries the independent pre-division pass in its CTAs >= nchunks:
+//   ghat[n,c] = grad_out[n,c] / max(count[n],1)   (div backward of back_project.py:72), re-packed to 16-byte aligned
+//   rows of C floats (grad_out rows are (C+1) floats and cannot be vector-loaded).
+__global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdParams p) {
   __shared__ int red[kScanThreads / 32];
   __shared__ int s_cid, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((int)blockIdx.x >= p.nchunks) {
+    const int C = p.C, C1 = C + 1;
+    const int64_t wg = (int64_t)(blockIdx.x - p.nchunks) * (kScanThreads / 32) + warp;
+    if ((C & 3) == 0 && C <= 128) {
+      // lane <-> (row, channel quad): 32/(C/4) rows per warp step, kGhatSteps steps in flight; 4 scalar loads (rows of
+      // C+1 floats are unaligned), one 128-bit store per lane
+      const int C4 = C >> 2;
+      const int rows_per_step = 32 / C4;
+      const int rl = lane / C4, j = lane - rl * C4;
+      const bool lane_on = rl < rows_per_step;
+      const int64_t r0 = wg * (int64_t)(rows_per_step * kGhatSteps) + rl;
+      float4 g[kGhatSteps];
+      float d[kGhatSteps];
+#pragma unroll
+      for (int k = 0; k < kGhatSteps; ++k) {
+        const int64_t r = r0 + (int64_t)k * rows_per_step;
+        g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        d[k] = 1.0f;
+        if (lane_on && r < p.N) {
+          const float* src = p.grad_out + r * C1 + 4 * j;
+          g[k] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+          d[k] = fmaxf(__ldg(p.count + r), 1.0f);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < kGhatSteps; ++k) {
+        const int64_t r = r0 + (int64_t)k * rows_per_step;
+        if (lane_on && r < p.N)
+          reinterpret_cast<float4*>(p.ghat)[r * C4 + j] =
+              make_float4(__fdiv_rn(g[k].x, d[k]), __fdiv_rn(g[k].y, d[k]), __fdiv_rn(g[k].z, d[k]), __fdiv_rn(g[k].w, d[k]));
+      }
+    } else {
+      // any C: warp per row, lanes stride over the channels
+      const int64_t r0 = wg * kGhatSteps;
+      for (int k = 0; k < kGhatSteps; ++k) {
+        const int64_t r = r0 + k;
+        if (r >= p.N) break;
+        const float d = fmaxf(__ldg(p.count + r), 1.0f);
+        for (int c = lane; c < C; c += 32) p.ghat[r * C + c] = __fdiv_rn(__ldg(p.grad_out + r * C1 + c), d);
+      }
+    }
+    return;
+  }
   if (tid == 0) s_cid = (int)atomicAdd(p.counter, 1u);
   __syncthreads();
   const int cid = s_cid;
@@ -189,186 +215,169 @@ __global__ void __launch_bounds__(kScanThreads) bp_scan_kernel(const BwdParams p
       st[cid] = (2ull << 32) | (unsigned)(prefix + total);
     }
     s_prefix = prefix;
-    if (cid == gridDim.x - 1) p.bin_start[p.M] = prefix + total;
+    if (cid == p.nchunks - 1) p.bin_start[p.M] = prefix + total;
   }
   __syncthreads();
   int off = s_prefix + woff + inc - s;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
-    if (base + i < p.M) p.bin_start[base + i] = off;
+    if (base + i < p.M) {
+      p.bin_start[base + i] = off;
+      p.bin_cursor[base + i] = off;
+    }
     off += v[i];
   }
 }
 
-// ---- order: sort each cell's entries by voxel index ---------------------------------------------
-__device__ __forceinline__ void bitonic_cell(volatile int4* E, int k, int lane) {
-  // all comparators ascending (mirror first stage), so virtual +inf padding above k never moves
-  int K2 = 1;
-  while (K2 < k) K2 <<= 1;
-  for (int sz = 2; sz <= K2; sz <<= 1) {
-    const int half = sz >> 1;
-    for (int i = lane; i < (K2 >> 1); i += 32) {
-      const int blk = i / half, off = i - blk * half;
-      const int lo = blk * sz + off, hi = blk * sz + sz - 1 - off;
-      if (hi < k) {
-        const int a = E[lo].x, b = E[hi].x;
-        if (a > b) {
-          const int4 ea = make_int4(E[lo].x, E[lo].y, E[lo].z, E[lo].w);
-          const int4 eb = make_int4(E[hi].x, E[hi].y, E[hi].z, E[hi].w);
-          E[lo].x = eb.x; E[lo].y = eb.y; E[lo].z = eb.z; E[lo].w = eb.w;
-          E[hi].x = ea.x; E[hi].y = ea.y; E[hi].z = ea.z; E[hi].w = ea.w;
-        }
-      }
+// ---- order: every cell's entries into ascending voxel order ----------------------------------------
+// One thread per entry, out of place: rank = number of entries of the same cell with a smaller voxel index (voxel
+// indices are unique within a cell because a voxel projects into a view at most once), destination = cell start +
+// rank.  The lanes of a warp mostly sit in the same cell, so the k reads of the rank loop are L1 broadcasts.
+// This removes the only nondeterminism of the backward pass (the claim order of the fill atomics).
+constexpr int kOrderThreads = 256;
+__global__ void __launch_bounds__(kOrderThreads) bp_bwd_order_kernel(const BwdParams p) {
+  const int total = __ldg(p.bin_start + p.M);
+  for (int i = blockIdx.x * kOrderThreads + threadIdx.x; i < total; i += gridDim.x * kOrderThreads) {
+    const int4 e = __ldg(p.entries + i);
+    const int ms = __ldg(p.bin_start + e.w), me = __ldg(p.bin_start + e.w + 1);
+    int rank = 0;
+    const int* keys = reinterpret_cast<const int*>(p.entries);
+    int j = ms;
+    for (; j + 4 <= me; j += 4) {
+      const int a0 = __ldg(keys + 4 * j), a1 = __ldg(keys + 4 * j + 4), a2 = __ldg(keys + 4 * j + 8),
+                a3 = __ldg(keys + 4 * j + 12);
+      rank += (a0 < e.x) + (a1 < e.x) + (a2 < e.x) + (a3 < e.x);
     }
-    __syncwarp();
-    for (int st = half >> 1; st >= 1; st >>= 1) {
-      for (int i = lane; i < (K2 >> 1); i += 32) {
-        const int blk = i / st, off = i - blk * st;
-        const int lo = blk * 2 * st + off, hi = lo + st;
-        if (hi < k) {
-          const int a = E[lo].x, b = E[hi].x;
-          if (a > b) {
-            const int4 ea = make_int4(E[lo].x, E[lo].y, E[lo].z, E[lo].w);
-            const int4 eb = make_int4(E[hi].x, E[hi].y, E[hi].z, E[hi].w);
-            E[lo].x = eb.x; E[lo].y = eb.y; E[lo].z = eb.z; E[lo].w = eb.w;
-            E[hi].x = ea.x; E[hi].y = ea.y; E[hi].z = ea.z; E[hi].w = ea.w;
-          }
-        }
-      }
-      __syncwarp();
-    }
-  }
-}
-
-
-constexpr int kOrderWindow = 256;  // entries staged per warp (4 KB of shared memory)
-
-// Each warp owns a run of cells.  Per iteration it stages a window of whole cells (<= 32 cells, <= 256 entries)
-// in shared memory, ranks every entry inside its own cell by counting smaller voxel indices (voxel indices are
-// unique within a cell), and writes the window back in ascending order.  Cells larger than the window fall
-// back to an in-place bitonic sort in global memory.
-__global__ void __launch_bounds__(256) bp_bwd_order_kernel(const BwdParams p, const int bins_per_task) {
-  __shared__ int4 s_ent[8][kOrderWindow];
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  int4* win = s_ent[wib];
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t ntasks = (p.M + bins_per_task - 1) / bins_per_task;
-  for (int64_t task = warp_global; task < ntasks; task += nwarps) {
-    int64_t bin = task * bins_per_task;
-    const int64_t bin_hi = min(p.M, bin + bins_per_task);
-    while (bin < bin_hi) {
-      const int64_t mb = bin + lane;  // lane l looks at cell bin+l
-      const bool have = mb < bin_hi;
-      const int sb = have ? __ldg(p.bin_start + mb) : 0x7fffffff;
-      const int eb = have ? __ldg(p.bin_start + mb + 1) : 0x7fffffff;
-      const int s0 = __shfl_sync(kFullB, sb, 0);
-      // whole cells that fit into the window starting at s0 (eb is monotone -> leading run of trues)
-      const unsigned fits = __ballot_sync(kFullB, have && (eb - s0) <= kOrderWindow);
-      const int nb = __popc(fits);
-      if (nb == 0) {  // first cell alone exceeds the window
-        const int e0 = __shfl_sync(kFullB, eb, 0);
-        bitonic_cell(reinterpret_cast<volatile int4*>(p.entries + s0), e0 - s0, lane);
-        bin += 1;
-        continue;
-      }
-      const int e_end = __shfl_sync(kFullB, eb, nb - 1);
-      const int total = e_end - s0;
-      const unsigned need = __ballot_sync(kFullB, lane < nb && (eb - sb) >= 2);
-      if (need != 0u) {
-        for (int i = lane; i < total; i += 32) win[i] = p.entries[s0 + i];
-        __syncwarp();
-        for (int i0 = 0; i0 < total; i0 += 32) {
-          const int i = i0 + lane;
-          const bool on = i < total;
-          const int pos = s0 + i;
-          // my cell: the last of the nb cells whose start is <= pos (empty cells share their successor's start)
-          int ms = s0, me = s0;
-          for (int l = 0; l < nb; ++l) {
-            const int vs_ = __shfl_sync(kFullB, sb, l), ve = __shfl_sync(kFullB, eb, l);
-            if (on && vs_ <= pos && pos < ve) { ms = vs_; me = ve; }
-          }
-          if (on && me - ms >= 2) {
-            const int4 e = win[i];
-            int rank = 0;
-            for (int j = ms - s0; j < me - s0; ++j) rank += (win[j].x < e.x) ? 1 : 0;
-            p.entries[ms + rank] = e;
-          }
-        }
-        __syncwarp();
-      }
-      bin += nb;
-    }
+    for (; j < me; ++j) rank += (__ldg(keys + 4 * j) < e.x) ? 1 : 0;
+    p.sorted[ms + rank] = e;
   }
 }
 
 // ---- gather --------------------------------------------------------------------------------------
+// Shared memory: part[4][ncell][C/4] float4 -- corner-major so that the lane groups of a warp (adjacent cells)
+// touch adjacent addresses in both phases (no bank conflicts, no padding).
 template <int G, int R>
-__global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_kernel(const BwdParams p) {
+__global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_tile_kernel(const BwdParams p, const int TX,
+                                                                               const int TY, const int tiles_x,
+                                                                               const int tiles_y) {
+  extern __shared__ __align__(16) unsigned char gsm[];
+  float4* part = reinterpret_cast<float4*>(gsm);
   constexpr int NG = 32 / G;
-  const int lane = threadIdx.x & 31;
+  constexpr int C4 = G * R;
+  constexpr int kGroups = kGatherWarps * NG;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / G, gl = lane % G;
-  const int C4 = p.C >> 2;
-  const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool gact = g < NG;
+  const int gid = warp * NG + g;
+  const int CW = TX + 1, CH = TY + 1, ncell = CW * CH;
+  int t = blockIdx.x;
+  const int txi = t % tiles_x; t /= tiles_x;
+  const int tyi = t % tiles_y;
+  const int map = t / tiles_y;
+  const int x0 = txi * TX, y0 = tyi * TY;
+  const int64_t map_base = (int64_t)map * p.H * p.W;
   const float4* __restrict__ ghat4 = reinterpret_cast<const float4*>(p.ghat);
-  float4* __restrict__ grad4 = reinterpret_cast<float4*>(p.grad_feats);
-  const int64_t nsteps = (p.M + NG - 1) / NG;
-  for (int64_t step = warp_global; step < nsteps; step += nwarps) {
-    const int64_t t = step * NG + g;
-    const bool gvalid = (g < NG) && (t < p.M);
-    const int x = gvalid ? (int)(t % p.W) : 0;
-    const int y = gvalid ? (int)((t / p.W) % p.H) : 0;
-    float4 acc[R];
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  // ---- phase 1: cells -> four corner partial sums each ------------------------------------------
+  for (int c0 = 0; c0 < ncell; c0 += kGroups) {
+    const int cl = c0 + gid;
+    const bool slot = gact && cl < ncell;
+    int s = 0, e = 0;
+    if (slot) {
+      const int cy = y0 - 1 + cl / CW, cx = x0 - 1 + cl % CW;
+      if (cy >= 0 && cx >= 0 && cy < p.H && cx < p.W) {
+        const int64_t cell = map_base + (int64_t)cy * p.W + cx;
+        s = __ldg(p.bin_start + cell);
+        e = __ldg(p.bin_start + cell + 1);
+      }
+    }
+    const int kmax = __reduce_max_sync(kFullB, e - s);
+    float4 anw[R], ane[R], asw[R], ase[R];
 #pragma unroll
-    for (int i = 0; i < R; ++i) acc[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int i = 0; i < R; ++i) { anw[i] = zero4; ane[i] = zero4; asw[i] = zero4; ase[i] = zero4; }
+    // Entries are taken BS at a time: lane j of the group fetches entry k0+j, the group then issues all BS row loads
+    // back to back (BS*R independent 128-bit loads in flight per lane) before the arithmetic, which runs in entry
+    // order.  The next batch's entries are fetched while the current rows are in flight.
+    constexpr int BS = (R == 1) ? (G < 8 ? G : 8) : (R == 2 ? 4 : 2);
+    const int gbase = g * G;
+    int4 mine = make_int4(-1, 0, 0, 0);
+    if (gl < BS && (s + gl) < e) mine = __ldg(p.sorted + s + gl);
+    for (int k0 = 0; k0 < kmax; k0 += BS) {
+      const int4 cur = mine;
+      mine = make_int4(-1, 0, 0, 0);
+      if (gl < BS && (s + k0 + BS + gl) < e) mine = __ldg(p.sorted + s + k0 + BS + gl);
+      float4 rows[BS][R];
+      float fxs[BS], fys[BS];
 #pragma unroll
-    for (int corner = 0; corner < 4; ++corner) {
-      // corner 0: this texel is the nw corner of cell (y,x); 1: ne of (y,x-1); 2: sw of (y-1,x); 3: se of (y-1,x-1)
-      const int dx = corner & 1, dy = corner >> 1;
-      const bool exists = gvalid && (x - dx >= 0) && (y - dy >= 0);
-      const int64_t cell = t - dx - (int64_t)dy * p.W;
-      int s = 0, e = 0;
-      if (exists) { s = __ldg(p.bin_start + cell); e = __ldg(p.bin_start + cell + 1); }
-      const int kmax = __reduce_max_sync(kFullB, e - s);
-      for (int k = 0; k < kmax; ++k) {
-        const bool on = (s + k) < e;
-        int4 en = make_int4(0, 0, 0, 0);
-        if (on) en = __ldg(p.entries + s + k);
-        const float fx = __int_as_float(en.y), fy = __int_as_float(en.z);
-        const float wx = dx ? fx : __fsub_rn(1.0f, fx);
-        const float wy = dy ? fy : __fsub_rn(1.0f, fy);
-        const float w = __fmul_rn(wx, wy);
-        const float4* row = ghat4 + (int64_t)en.x * C4 + gl;
+      for (int j = 0; j < BS; ++j) {
+        const int nj = __shfl_sync(kFullB, cur.x, gbase + j);
+        fxs[j] = __int_as_float(__shfl_sync(kFullB, cur.y, gbase + j));
+        fys[j] = __int_as_float(__shfl_sync(kFullB, cur.z, gbase + j));
+        const bool on = gact && nj >= 0;
+        const float4* row = ghat4 + (int64_t)(on ? nj : 0) * C4 + gl;
+#pragma unroll
+        for (int i = 0; i < R; ++i) rows[j][i] = on ? __ldg(row + i * G) : zero4;
+      }
+#pragma unroll
+      for (int j = 0; j < BS; ++j) {
+        // an absent entry has a zero row: it adds +0 to every sum (no branch needed)
+        const float fx = fxs[j], fy = fys[j];
+        const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy);
+        const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(fx, wy0), sw = __fmul_rn(wx0, fy), se = __fmul_rn(fx, fy);
 #pragma unroll
         for (int i = 0; i < R; ++i) {
-          if (on) {
-            const float4 gq = __ldg(row + i * G);
-            acc[i].x = __fadd_rn(acc[i].x, __fmul_rn(w, gq.x));
-            acc[i].y = __fadd_rn(acc[i].y, __fmul_rn(w, gq.y));
-            acc[i].z = __fadd_rn(acc[i].z, __fmul_rn(w, gq.z));
-            acc[i].w = __fadd_rn(acc[i].w, __fmul_rn(w, gq.w));
-          }
+          const float4 q = rows[j][i];
+          anw[i].x = __fadd_rn(anw[i].x, __fmul_rn(nw, q.x)); anw[i].y = __fadd_rn(anw[i].y, __fmul_rn(nw, q.y));
+          anw[i].z = __fadd_rn(anw[i].z, __fmul_rn(nw, q.z)); anw[i].w = __fadd_rn(anw[i].w, __fmul_rn(nw, q.w));
+          ane[i].x = __fadd_rn(ane[i].x, __fmul_rn(ne, q.x)); ane[i].y = __fadd_rn(ane[i].y, __fmul_rn(ne, q.y));
+          ane[i].z = __fadd_rn(ane[i].z, __fmul_rn(ne, q.z)); ane[i].w = __fadd_rn(ane[i].w, __fmul_rn(ne, q.w));
+          asw[i].x = __fadd_rn(asw[i].x, __fmul_rn(sw, q.x)); asw[i].y = __fadd_rn(asw[i].y, __fmul_rn(sw, q.y));
+          asw[i].z = __fadd_rn(asw[i].z, __fmul_rn(sw, q.z)); asw[i].w = __fadd_rn(asw[i].w, __fmul_rn(sw, q.w));
+          ase[i].x = __fadd_rn(ase[i].x, __fmul_rn(se, q.x)); ase[i].y = __fadd_rn(ase[i].y, __fmul_rn(se, q.y));
+          ase[i].z = __fadd_rn(ase[i].z, __fmul_rn(se, q.z)); ase[i].w = __fadd_rn(ase[i].w, __fmul_rn(se, q.w));
         }
       }
     }
-    if (gvalid) {
+    if (slot) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        const int o = cl * C4 + i * G + gl;
+        part[o] = anw[i];
+        part[ncell * C4 + o] = ane[i];
+        part[2 * ncell * C4 + o] = asw[i];
+        part[3 * ncell * C4 + o] = ase[i];
+      }
+    }
+  }
+  __syncthreads();
+  // ---- phase 2: texel (y,x) = nw(y,x) + ne(y,x-1) + sw(y-1,x) + se(y-1,x-1), in that order ---------
+  const int64_t hw = (int64_t)p.H * p.W;
+  for (int q0 = 0; q0 < TX * TY; q0 += kGroups) {
+    const int q = q0 + gid;
+    if (!gact || q >= TX * TY) continue;
+    const int ty = q / TX, tx = q - ty * TX;
+    const int y = y0 + ty, x = x0 + tx;
+    if (y >= p.H || x >= p.W) continue;
+    const int cnw = (ty + 1) * CW + tx + 1, cne = cnw - 1, csw = cnw - CW, cse = csw - 1;
+    const int64_t tex = map_base + (int64_t)y * p.W + x;
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const int o = i * G + gl;
+      float4 a = part[cnw * C4 + o];
+      const float4 b1 = part[(ncell + cne) * C4 + o];
+      const float4 b2 = part[(2 * ncell + csw) * C4 + o];
+      const float4 b3 = part[(3 * ncell + cse) * C4 + o];
+      a.x = __fadd_rn(__fadd_rn(__fadd_rn(a.x, b1.x), b2.x), b3.x);
+      a.y = __fadd_rn(__fadd_rn(__fadd_rn(a.y, b1.y), b2.y), b3.y);
+      a.z = __fadd_rn(__fadd_rn(__fadd_rn(a.z, b1.z), b2.z), b3.z);
+      a.w = __fadd_rn(__fadd_rn(__fadd_rn(a.w, b1.w), b2.w), b3.w);
       if (!p.grad_nchw) {
-#pragma unroll
-        for (int i = 0; i < R; ++i) grad4[t * C4 + i * G + gl] = acc[i];
+        reinterpret_cast<float4*>(p.grad_feats)[tex * C4 + o] = a;
       } else {
-        // (V,B,C,H,W): texel t = (vb, y, x) -> channel c lives at ((vb*C + c)*H + y)*W + x
-        const int64_t hw = (int64_t)p.H * p.W;
-        const int64_t vb = t / hw, yx = t - vb * hw;
-        float* dst = p.grad_feats + vb * p.C * hw + yx;
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const int c0 = (i * G + gl) * 4;
-          dst[(int64_t)(c0 + 0) * hw] = acc[i].x;
-          dst[(int64_t)(c0 + 1) * hw] = acc[i].y;
-          dst[(int64_t)(c0 + 2) * hw] = acc[i].z;
-          dst[(int64_t)(c0 + 3) * hw] = acc[i].w;
-        }
+        // (V,B,C,H,W): channel c of texel (map, y, x) lives at ((map*C + c)*H + y)*W + x
+        float* dst = p.grad_feats + (int64_t)map * p.C * hw + (int64_t)y * p.W + x + (int64_t)(o * 4) * hw;
+        dst[0] = a.x; dst[hw] = a.y; dst[2 * hw] = a.z; dst[3 * hw] = a.w;
       }
     }
   }
@@ -392,7 +401,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_generic_kerne
       const int64_t cell = t - dx - (int64_t)dy * p.W;
       const int s = __ldg(p.bin_start + cell), e = __ldg(p.bin_start + cell + 1);
       for (int k = s; k < e; ++k) {
-        const int4 en = __ldg(p.entries + k);
+        const int4 en = __ldg(p.sorted + k);
         const float fx = __int_as_float(en.y), fy = __int_as_float(en.z);
         const float wx = dx ? fx : __fsub_rn(1.0f, fx);
         const float wy = dy ? fy : __fsub_rn(1.0f, fy);
@@ -423,7 +432,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_generic_kerne
 
 // ---- host ----------------------------------------------------------------------------------------
 struct BwdWs {
-  size_t ghat, cnt, bin_cnt, bin_start, scan_state, counter, entries, total, zero_bytes;
+  size_t ghat, cnt, bin_cnt, bin_cursor, bin_start, scan_state, counter, entries, sorted, total, zero_bytes;
   int nchunks;
   int64_t M;
 };
@@ -436,26 +445,26 @@ static BwdWs bwd_ws_layout(int64_t N, int B, int V, int C, int H, int W) {
   const size_t n1 = (size_t)(N > 0 ? N : 1);
   w.ghat = o; o = align_up(o + sizeof(float) * n1 * (size_t)C, 256);
   w.cnt = o; o = align_up(o + sizeof(float) * n1, 256);
-  w.bin_cnt = o; o = align_up(o + sizeof(int) * (size_t)w.M, 256);
+  // scan_state and the ticket are cleared by ONE memset; bin_cnt follows them so that the same memset also
+  // clears the histogram when the forward pass did not hand one over
   w.scan_state = o; o = align_up(o + sizeof(unsigned long long) * (size_t)(w.nchunks + 1), 256);
   w.counter = o; o = align_up(o + 256, 256);
-  w.zero_bytes = o - w.bin_cnt;  // bin_cnt, scan_state and the ticket are cleared by ONE memset
+  w.bin_cnt = o; o = align_up(o + sizeof(int) * (size_t)w.M, 256);
+  w.zero_bytes = o - w.scan_state;
+  w.bin_cursor = o; o = align_up(o + sizeof(int) * (size_t)w.M, 256);
   w.bin_start = o; o = align_up(o + sizeof(int) * (size_t)(w.M + 1), 256);
   w.entries = o; o = align_up(o + sizeof(int4) * n1 * (size_t)V, 256);
+  w.sorted = o; o = align_up(o + sizeof(int4) * n1 * (size_t)V, 256);
   w.total = o;
   return w;
 }
 
-typedef void (*gather_kernel_t)(const BwdParams);
-static gather_kernel_t pick_gather_kernel(int C, int& NG) {
-  NG = 1;
+typedef void (*gather_kernel_t)(const BwdParams, int, int, int, int);
+static gather_kernel_t pick_gather_kernel(int C) {
   if (C % 4 != 0) return nullptr;
   const int q = C / 4;
-#define D3M_BWD_CASE(g, r)              \
-  if (q == (g) * (r)) {                 \
-    NG = 32 / (g);                      \
-    return bp_bwd_gather_kernel<g, r>;  \
-  }
+#define D3M_BWD_CASE(g, r) \
+  if (q == (g) * (r)) return bp_bwd_gather_tile_kernel<g, r>;
   D3M_BWD_CASE(6, 1)
   D3M_BWD_CASE(10, 1)
   D3M_BWD_CASE(10, 2)
@@ -471,28 +480,42 @@ static gather_kernel_t pick_gather_kernel(int C, int& NG) {
   return nullptr;
 }
 
+// texel tile of the gather kernel: the largest of a fixed ladder whose 4 x (TX+1)(TY+1) x C floats fit the budget
+static void pick_gather_tile(int C, int H, int W, int& TX, int& TY, size_t& smem) {
+  static const int ladder[][2] = {{16, 8}, {8, 8}, {8, 4}, {4, 4}, {2, 2}, {1, 1}};
+  const size_t budget = 64 * 1024;
+  for (auto& t : ladder) {
+    TX = t[0]; TY = t[1];
+    smem = (size_t)16 * C * (TX + 1) * (TY + 1);
+    if (smem <= budget) break;
+  }
+  (void)H; (void)W;
+}
+
 template <int KIND>
-static int launch_bwd(const BwdParams& p, size_t zero_bytes, float* cnt_ws, cudaStream_t stream) {
+static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bool have_hist, float* cnt_ws,
+                      cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  D3M_CUDA_CHECK(cudaMemsetAsync(p.bin_cnt, 0, zero_bytes, stream));
+  D3M_CUDA_CHECK(cudaMemsetAsync(zero_from, 0, zero_bytes, stream));
   const unsigned vox_ctas = (unsigned)((p.N + kSampleThreads - 1) / kSampleThreads);
   if (cnt_ws) {  // no forward count handed over: recompute it
     LaunchScope ls("bp_bwd_count", stream);
     bp_bwd_count_kernel<KIND><<<vox_ctas, kSampleThreads, 0, stream>>>(p, cnt_ws);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
-  {
-    const int64_t ghat_blocks = (p.N * p.C + kSampleThreads * kGhatPerThread - 1) / (kSampleThreads * kGhatPerThread);
-    const unsigned ghat_rows = (unsigned)((ghat_blocks + vox_ctas - 1) / vox_ctas);
-    LaunchScope ls("bp_bwd_hist_ghat", stream);
-    bp_bwd_sample_kernel<KIND, false><<<dim3(vox_ctas, p.V + ghat_rows), kSampleThreads, 0, stream>>>(p);
+  if (!have_hist) {
+    LaunchScope ls("bp_bwd_hist", stream);
+    bp_bwd_sample_kernel<KIND, false><<<dim3(vox_ctas, p.V), kSampleThreads, 0, stream>>>(p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
-    LaunchScope ls("bp_bwd_scan", stream);
-    bp_scan_kernel<<<p.nchunks, kScanThreads, 0, stream>>>(p);
+    const int rows_per_step = ((p.C & 3) == 0 && p.C <= 128) ? 32 / (p.C >> 2) : 1;
+    const int64_t rows_per_cta = (int64_t)(kScanThreads / 32) * kGhatSteps * rows_per_step;
+    const int64_t ghat_blocks = (p.N + rows_per_cta - 1) / rows_per_cta;
+    LaunchScope ls("bp_bwd_scan_ghat", stream);
+    bp_scan_ghat_kernel<<<(unsigned)(p.nchunks + ghat_blocks), kScanThreads, 0, stream>>>(p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
@@ -501,31 +524,32 @@ static int launch_bwd(const BwdParams& p, size_t zero_bytes, float* cnt_ws, cuda
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
-    // cells per warp task: small enough that even the coarsest level spreads over every SM
-    int bins = (int)(p.M / ((int64_t)sms * 32));
-    bins = bins < 8 ? 8 : (bins > 256 ? 256 : bins);
-    const int64_t ntasks = (p.M + bins - 1) / bins;
-    int64_t ctas = (ntasks + 7) / 8;
-    if (ctas > (int64_t)sms * 64) ctas = (int64_t)sms * 64;
+    int64_t ctas = (p.N * p.V + kOrderThreads - 1) / kOrderThreads;  // upper bound of the entry count (known on device only)
+    if (ctas > (int64_t)sms * 16) ctas = (int64_t)sms * 16;
     if (ctas < 1) ctas = 1;
     LaunchScope ls("bp_bwd_order", stream);
-    bp_bwd_order_kernel<<<(unsigned)ctas, 256, 0, stream>>>(p, bins);
+    bp_bwd_order_kernel<<<(unsigned)ctas, kOrderThreads, 0, stream>>>(p);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
-  {
-    int NG;
-    gather_kernel_t k = pick_gather_kernel(p.C, NG);
-    if (!k) {
-      D3M_REQUIRE(p.C <= 256, D3M_ERR_ARG, "back_project backward: C=%d unsupported (C%%4!=0 needs C<=256)", p.C);
-      k = bp_bwd_gather_generic_kernel;
-      NG = 1;
-    }
-    const int64_t nsteps = (p.M + NG - 1) / NG;
-    int64_t ctas = (nsteps + kGatherWarps - 1) / kGatherWarps;
+  gather_kernel_t k = pick_gather_kernel(p.C);
+  if (k) {
+    int TX, TY;
+    size_t smem;
+    pick_gather_tile(p.C, p.H, p.W, TX, TY, smem);
+    const int tiles_x = (p.W + TX - 1) / TX, tiles_y = (p.H + TY - 1) / TY;
+    const int64_t tiles = (int64_t)p.V * p.B * tiles_x * tiles_y;
+    D3M_REQUIRE(tiles < (1ll << 31), D3M_ERR_ARG, "back_project backward: too many gather tiles");
+    D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    LaunchScope ls("bp_bwd_gather", stream);
+    k<<<(unsigned)tiles, kGatherWarps * 32, smem, stream>>>(p, TX, TY, tiles_x, tiles_y);
+    D3M_CUDA_CHECK(cudaGetLastError());
+  } else {
+    D3M_REQUIRE(p.C <= 256, D3M_ERR_ARG, "back_project backward: C=%d unsupported (C%%4!=0 needs C<=256)", p.C);
+    int64_t ctas = (p.M + kGatherWarps - 1) / kGatherWarps;
     if (ctas > (int64_t)sms * 16) ctas = (int64_t)sms * 16;
     if (ctas < 1) ctas = 1;
     LaunchScope ls("bp_bwd_gather", stream);
-    k<<<(unsigned)ctas, kGatherWarps * 32, 0, stream>>>(p);
+    bp_bwd_gather_generic_kernel<<<(unsigned)ctas, kGatherWarps * 32, 0, stream>>>(p);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
   return D3M_OK;
@@ -542,8 +566,9 @@ extern "C" size_t d3m_back_project_bwd_workspace(int64_t N, int B, int V, int C,
 
 extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                                     float voxel_size, int V, int C, int H, int W, const float* KRcam,
-                                    const float* grad_out, const float* count, float* grad_feats_nhwc, int grad_nchw,
-                                    void* workspace, size_t workspace_bytes, void* stream_) {
+                                    const float* grad_out, const float* count, const int* cell_hist,
+                                    float* grad_feats_nhwc, int grad_nchw, void* workspace, size_t workspace_bytes,
+                                    void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE,
               "back_project backward: no CUDA device (there is no CPU fallback)");
@@ -551,7 +576,7 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
               "back_project backward: bad sizes N=%lld B=%d V=%d C=%d H=%d W=%d", (long long)N, B, V, C, H, W);
   D3M_REQUIRE(coords_kind >= 0 && coords_kind <= 2, D3M_ERR_ARG, "back_project backward: coords_kind=%d", coords_kind);
   D3M_REQUIRE((int64_t)V * B * H * W < (1ll << 30), D3M_ERR_ARG, "back_project backward: V*B*H*W must be < 2^30");
-  D3M_REQUIRE(V <= 65535 - 4096, D3M_ERR_ARG, "back_project backward: too many views");
+  D3M_REQUIRE(V <= 65535, D3M_ERR_ARG, "back_project backward: too many views");
   D3M_REQUIRE(N * (int64_t)V < (1ll << 31), D3M_ERR_ARG, "back_project backward: N*V must be < 2^31 samples");
   D3M_REQUIRE(grad_feats_nhwc && workspace, D3M_ERR_ARG, "back_project backward: NULL pointer");
   const BwdWs w = bwd_ws_layout(N, B, V, C, H, W);
@@ -560,8 +585,9 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
     return D3M_OK;
   }
   D3M_REQUIRE(coords && origin && KRcam && grad_out, D3M_ERR_ARG, "back_project backward: NULL pointer");
-  D3M_REQUIRE(aligned16(coords) && aligned16(KRcam) && aligned16(grad_feats_nhwc) && aligned16(workspace),
-              D3M_ERR_ALIGN, "back_project backward: coords/KRcam/grad_feats/workspace must be 16-byte aligned");
+  D3M_REQUIRE(aligned16(coords) && aligned16(KRcam) && aligned16(grad_feats_nhwc) && aligned16(workspace) &&
+                  aligned16(cell_hist),
+              D3M_ERR_ALIGN, "back_project backward: coords/KRcam/grad_feats/cell_hist/workspace must be 16-byte aligned");
   D3M_REQUIRE(workspace_bytes >= w.total, D3M_ERR_WORKSPACE, "back_project backward: workspace %zu < %zu",
               workspace_bytes, w.total);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
@@ -569,18 +595,24 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
   p.coords = coords; p.N = N; p.origin = origin; p.B = B; p.vs = voxel_size;
   p.V = V; p.C = C; p.H = H; p.W = W; p.KR = KRcam; p.grad_out = grad_out;
   p.ghat = reinterpret_cast<float*>(ws + w.ghat);
-  p.bin_cnt = reinterpret_cast<int*>(ws + w.bin_cnt);
+  // with a forward-pass histogram the workspace copy is unused and only scan_state + ticket need clearing
+  p.bin_cnt = cell_hist ? const_cast<int*>(cell_hist) : reinterpret_cast<int*>(ws + w.bin_cnt);
+  p.bin_cursor = reinterpret_cast<int*>(ws + w.bin_cursor);
   p.bin_start = reinterpret_cast<int*>(ws + w.bin_start);
   p.scan_state = reinterpret_cast<unsigned long long*>(ws + w.scan_state);
   p.counter = reinterpret_cast<unsigned int*>(ws + w.counter);
   p.entries = reinterpret_cast<int4*>(ws + w.entries);
+  p.sorted = reinterpret_cast<int4*>(ws + w.sorted);
   p.grad_feats = grad_feats_nhwc;
   p.M = w.M;
   p.nchunks = w.nchunks;
   p.grad_nchw = grad_nchw ? 1 : 0;
   float* cnt_ws = count ? nullptr : reinterpret_cast<float*>(ws + w.cnt);
   p.count = count ? count : cnt_ws;
-  if (coords_kind == D3M_COORDS_F32) return launch_bwd<D3M_COORDS_F32>(p, w.zero_bytes, cnt_ws, stream);
-  if (coords_kind == D3M_COORDS_I64) return launch_bwd<D3M_COORDS_I64>(p, w.zero_bytes, cnt_ws, stream);
-  return launch_bwd<D3M_COORDS_I32>(p, w.zero_bytes, cnt_ws, stream);
+  void* zero_from = ws + w.scan_state;
+  const size_t zero_bytes = cell_hist ? (w.bin_cnt - w.scan_state) : w.zero_bytes;
+  const bool hh = cell_hist != nullptr;
+  if (coords_kind == D3M_COORDS_F32) return launch_bwd<D3M_COORDS_F32>(p, zero_from, zero_bytes, hh, cnt_ws, stream);
+  if (coords_kind == D3M_COORDS_I64) return launch_bwd<D3M_COORDS_I64>(p, zero_from, zero_bytes, hh, cnt_ws, stream);
+  return launch_bwd<D3M_COORDS_I32>(p, zero_from, zero_bytes, hh, cnt_ws, stream);
 }

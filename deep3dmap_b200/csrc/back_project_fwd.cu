@@ -12,6 +12,9 @@
 //   flush    the tile's (tv, C+1) rows are staged in shared memory and leave with ONE bulk async copy
 //            (cp.async.bulk, TMA engine) because (C+1)-float rows cannot be written with aligned vectors.
 // Arithmetic order is the oracle's (oracle/d3m_oracle.c) so features and counts are bit-identical to it.
+#include <stdlib.h>
+#include <string.h>
+
 #include "d3m_common.cuh"
 
 namespace d3m {
@@ -37,6 +40,7 @@ struct FwdParams {
   float* zbar;
   int* bidx;
   unsigned int* counter;  // zeroed here for the stats kernel
+  int* cell_hist;         // optional (V*B*H*W) histogram of valid samples per bilinear cell, consumed by the backward pass
   int tv;
   int vchunk;
   int64_t num_tiles;
@@ -70,6 +74,7 @@ __device__ __forceinline__ int push_records(const FwdParams& p, int b, float gx,
       const Sample s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
       if (s.valid) {
         int off = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
+        if (p.cell_hist) atomicAdd(p.cell_hist + off, 1);  // integer RED: order-independent
         if (s.x0 + 1 < p.W) off |= kFlagX1;
         if (s.y0 + 1 < p.H) off |= kFlagY1;
         rec_off[ccnt * 32 + lane] = off;
@@ -396,12 +401,16 @@ __global__ void __launch_bounds__(kStatsThreads) bp_stats_kernel(const StatsPara
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  for (int b = tid; b < p.B; b += kStatsThreads) {
+  // fixed-shape fold: warp w takes fragments w, w+8, ...; lane l sums chunks l, l+32, ... in order, then one
+  // shuffle tree -- the shape depends on nchunks only, never on which CTA happened to arrive last
+  for (int b = warp; b < p.B; b += kStatsThreads / 32) {
     double s = 0.0, s2 = 0.0, c = 0.0;
-    for (int k = 0; k < p.nchunks; ++k) {
-      const volatile double* q = p.partial + ((size_t)k * p.B + b) * 3;
-      s += q[0]; s2 += q[1]; c += q[2];
+    for (int k = lane; k < p.nchunks; k += 32) {
+      const double* q = p.partial + ((size_t)k * p.B + b) * 3;
+      s += __ldcg(q); s2 += __ldcg(q + 1); c += __ldcg(q + 2);
     }
+    s = warp_sum(s); s2 = warp_sum(s2); c = warp_sum(c);
+    if (lane != 0) continue;
     if (p.sums) { p.sums[3 * b] = s; p.sums[3 * b + 1] = s2; p.sums[3 * b + 2] = c; }
     if (p.finalize) {
       float mean, sd;
@@ -466,30 +475,40 @@ static FwdWs fwd_ws_layout(int64_t N, int B) {
 
 typedef void (*fwd_kernel_t)(const FwdParams);
 
+// (G lanes x R float4 per lane) = C/4 channel quads per voxel.  The table lists every instantiated shape; for a given
+// C the FIRST matching row is the default, D3M_FWD_GR="C:G:R[,C:G:R...]" (tuning aid) selects another one.
 template <int KIND>
 static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
-  // (G lanes x R float4 per lane) = C/4 chunks; prefer the widest group that keeps >= 30/32 lanes busy
+  struct Row { int g, r; fwd_kernel_t k; };
+#define D3M_FWD_ROW(g, r) {g, r, bp_fwd_kernel<KIND, g, r>}
+  static const Row rows[] = {
+      D3M_FWD_ROW(6, 1),  D3M_FWD_ROW(3, 2),  D3M_FWD_ROW(2, 3),                    // C = 24  (level 2)
+      D3M_FWD_ROW(10, 1), D3M_FWD_ROW(5, 2),  D3M_FWD_ROW(2, 5),                    // C = 40  (level 1)
+      D3M_FWD_ROW(10, 2), D3M_FWD_ROW(5, 4),  D3M_FWD_ROW(4, 5),                    // C = 80  (level 0)
+      D3M_FWD_ROW(4, 1),  D3M_FWD_ROW(8, 1),  D3M_FWD_ROW(16, 1), D3M_FWD_ROW(8, 3), D3M_FWD_ROW(16, 2),
+      D3M_FWD_ROW(2, 1),  D3M_FWD_ROW(3, 1),  D3M_FWD_ROW(5, 1)};
+#undef D3M_FWD_ROW
   G = 0; R = 0;
   if (C % 4 != 0) return nullptr;
   const int q = C / 4;
-#define D3M_FWD_CASE(g, r)            \
-  if (q == (g) * (r)) {               \
-    G = (g); R = (r);                 \
-    return bp_fwd_kernel<KIND, g, r>; \
+  int want_g = 0, want_r = 0;
+  if (const char* env = getenv("D3M_FWD_GR")) {
+    for (const char* s = env; s && *s;) {
+      int c = 0, g = 0, r = 0;
+      if (sscanf(s, "%d:%d:%d", &c, &g, &r) == 3 && c == C) { want_g = g; want_r = r; }
+      s = strchr(s, ',');
+      if (s) ++s;
+    }
   }
-  D3M_FWD_CASE(6, 1)    // C = 24  (level 2)
-  D3M_FWD_CASE(10, 1)   // C = 40  (level 1)
-  D3M_FWD_CASE(10, 2)   // C = 80  (level 0)
-  D3M_FWD_CASE(4, 1)    // C = 16
-  D3M_FWD_CASE(8, 1)    // C = 32
-  D3M_FWD_CASE(16, 1)   // C = 64
-  D3M_FWD_CASE(8, 3)    // C = 96
-  D3M_FWD_CASE(16, 2)   // C = 128
-  D3M_FWD_CASE(2, 1)    // C = 8
-  D3M_FWD_CASE(3, 1)    // C = 12
-  D3M_FWD_CASE(5, 1)    // C = 20
-#undef D3M_FWD_CASE
-  return nullptr;
+  const Row* pick = nullptr;
+  for (const Row& row : rows) {
+    if (row.g * row.r != q) continue;
+    if (!pick) pick = &row;
+    if (row.g == want_g && row.r == want_r) { pick = &row; break; }
+  }
+  if (!pick) return nullptr;
+  G = pick->g; R = pick->r;
+  return pick->k;
 }
 
 template <int KIND>
@@ -570,10 +589,14 @@ static int fwd_normalise(int64_t N, int C, const FwdWs& w, unsigned char* ws, fl
 // channel is left un-normalised until d3m_back_project_fwd_finish.
 static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float* origin, int B, float voxel_size,
                     const float* feats_nhwc, int V, int C, int H, int W, const float* KRcam, float* out, float* count,
-                    void* workspace, size_t workspace_bytes, double* depth_sums, cudaStream_t stream) {
+                    int* cell_hist, void* workspace, size_t workspace_bytes, double* depth_sums, cudaStream_t stream) {
   int rc = fwd_check(coords, coords_kind, N, origin, B, feats_nhwc, V, C, H, W, KRcam, out, count, workspace,
                      workspace_bytes);
   if (rc != D3M_OK) return rc;
+  if (cell_hist) {
+    D3M_REQUIRE(aligned16(cell_hist), D3M_ERR_ALIGN, "back_project: cell_hist must be 16-byte aligned");
+    D3M_CUDA_CHECK(cudaMemsetAsync(cell_hist, 0, sizeof(int) * (size_t)V * B * H * W, stream));
+  }
   if (N == 0) {
     if (depth_sums) D3M_CUDA_CHECK(cudaMemsetAsync(depth_sums, 0, sizeof(double) * 3 * (size_t)B, stream));
     return D3M_OK;
@@ -583,7 +606,7 @@ static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float*
   FwdParams p;
   p.coords = coords; p.N = N; p.origin = origin; p.B = B; p.vs = voxel_size;
   p.feats = feats_nhwc; p.V = V; p.C = C; p.H = H; p.W = W; p.KR = KRcam;
-  p.out = out; p.count = count;
+  p.out = out; p.count = count; p.cell_hist = cell_hist;
   p.zbar = reinterpret_cast<float*>(ws + w.zbar);
   p.bidx = reinterpret_cast<int*>(ws + w.bidx);
   p.counter = reinterpret_cast<unsigned int*>(ws + w.counter);
@@ -609,19 +632,20 @@ static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float*
 
 extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                                     float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                                    const float* KRcam, float* out, float* count, void* workspace,
+                                    const float* KRcam, float* out, float* count, int* cell_hist, void* workspace,
                                     size_t workspace_bytes, void* stream_) {
-  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats_nhwc, V, C, H, W, KRcam, out, count, workspace,
-                  workspace_bytes, nullptr, static_cast<cudaStream_t>(stream_));
+  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats_nhwc, V, C, H, W, KRcam, out, count, cell_hist,
+                  workspace, workspace_bytes, nullptr, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int d3m_back_project_fwd_partial(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                                             float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                                            const float* KRcam, float* out, float* count, double* depth_sums,
-                                            void* workspace, size_t workspace_bytes, void* stream_) {
+                                            const float* KRcam, float* out, float* count, int* cell_hist,
+                                            double* depth_sums, void* workspace, size_t workspace_bytes,
+                                            void* stream_) {
   D3M_REQUIRE(depth_sums, D3M_ERR_ARG, "back_project_fwd_partial: NULL depth_sums");
-  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats_nhwc, V, C, H, W, KRcam, out, count, workspace,
-                  workspace_bytes, depth_sums, static_cast<cudaStream_t>(stream_));
+  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats_nhwc, V, C, H, W, KRcam, out, count, cell_hist,
+                  workspace, workspace_bytes, depth_sums, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sums, float* out,

@@ -15,6 +15,7 @@
 // source compiled verbatim, see oracle/build_ref.py and tests/test_gpu_tsdf.py).
 // Deliberate deviation: integer index decomposition (the reference's float one, :89-91, breaks for > 2^24 voxels).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -24,7 +25,7 @@
 namespace d3m {
 
 constexpr int kTileX = 8, kTileY = 8, kTileZ = 16;
-constexpr int kTsdfThreads = 256;         // (z:16) x (y:8) x (x-group:2), 4 x-planes per thread
+constexpr int kTsdfThreads = 256;         // 8 warps = 2x2x2 sub-boxes of 4x4x8 voxels; a lane owns 4 x-planes of one (y,z)
 constexpr int kVoxPerThread = 4;
 constexpr int kMaxFramesPerLaunch = 1024;
 constexpr int kPrepParts = 16;
@@ -48,6 +49,9 @@ struct TsdfParams {
   float* color;
   int dx, dy, dz;
   int xoff;             // global x index of local plane 0 (slab sharding), 0 otherwise
+  int variant;          // tuning switches (D3M_TSDF_VARIANT, default 0): 1 = warp-level frame cull, 2 = division-free
+                        // quick reject.  Both were measured SLOWER on B200 (profiles/r01_tsdf_variants.txt): the extra
+                        // tests cost more issue slots than the divisions they save
   float ox, oy, oz, vs, trunc;
   const Frame* frames;
   int F;
@@ -65,7 +69,12 @@ __global__ void __launch_bounds__(256) tsdf_prep_kernel(const float* __restrict_
   const int per = (HW + kPrepParts - 1) / kPrepParts;
   const int i0 = part * per, i1 = min(HW, i0 + per);
   float m = 0.0f;
-  for (int i = i0 + threadIdx.x; i < i1; i += 256) m = fmaxf(m, __ldg(d + i));  // NaN-ignoring max
+  for (int i = i0 + threadIdx.x; i < i1; i += 256) {
+    // a NaN depth passes the reference's `depth == 0` / `diff < -trunc` tests (tsdf_volume.py:114,119), so it can
+    // update voxels at any distance: disable the far cull for such a frame instead of ignoring the pixel
+    const float v = __ldg(d + i);
+    m = (v != v) ? INFINITY : fmaxf(m, v);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
@@ -131,10 +140,25 @@ __device__ __forceinline__ bool tile_hits_frame(const Frame& fr, float zmaxd, fl
 // PTX cvt.rzi.s32.f32 is what `(int)` compiles to: saturating, NaN -> 0 (same as in the reference kernel)
 __device__ __forceinline__ int f2i_rz(float x) { return __float2int_rz(x); }
 
+// Division-free conservative rejection: true only for voxels the exact arithmetic below certainly skips -- behind the
+// camera, a full pixel outside the image (the exact test rounds to the nearest pixel, i.e. has a half-pixel band), or
+// so far behind the deepest measurement of the frame that depth - cam_z < -trunc for every pixel.  Voxels near any
+// boundary fall through to the exact reference arithmetic, so results are unchanged bit for bit.
+__device__ __forceinline__ bool quick_reject(const Frame& fr, float camx, float camy, float camz, float zfar, float W,
+                                             float H) {
+  if (camz < 0.0f || camz > zfar) return true;
+  const float ax = fr.fx * camx, ay = fr.fy * camy;
+  if (ax + (fr.cx + 1.0f) * camz < 0.0f) return true;   // u < -1
+  if (ax + (fr.cx - W) * camz > 0.0f) return true;      // u > W
+  if (ay + (fr.cy + 1.0f) * camz < 0.0f) return true;   // v < -1
+  if (ay + (fr.cy - H) * camz > 0.0f) return true;      // v > H
+  return false;
+}
+
 template <int SEM, bool COLOR>
 __device__ __forceinline__ void integrate_voxel(const TsdfParams& p, const Frame& fr, const float* __restrict__ depth,
-                                                const float* __restrict__ cimg, float vx, float vy, float vz,
-                                                float& tsdf, float& w, float& col, bool& dirty) {
+                                                const float* __restrict__ cimg, float zfar, float vx, float vy,
+                                                float vz, float& tsdf, float& w, float& col, bool& dirty) {
   float camx, camy, camz;
   int px, py;
   bool ok;
@@ -145,6 +169,7 @@ __device__ __forceinline__ void integrate_voxel(const TsdfParams& p, const Frame
     camx = __fmaf_rn(tz, fr.T[8], __fmaf_rn(tx, fr.T[0], __fmul_rn(ty, fr.T[4])));
     camy = __fmaf_rn(tz, fr.T[9], __fmaf_rn(tx, fr.T[1], __fmul_rn(ty, fr.T[5])));
     camz = __fmaf_rn(tz, fr.T[10], __fmaf_rn(tx, fr.T[2], __fmul_rn(ty, fr.T[6])));
+    if ((p.variant & 2) && quick_reject(fr, camx, camy, camz, zfar, (float)p.W, (float)p.H)) return;
     px = f2i_rz(roundf(__fmaf_rn(fr.fx, __fdiv_rn(camx, camz), fr.cx)));
     py = f2i_rz(roundf(__fmaf_rn(fr.fy, __fdiv_rn(camy, camz), fr.cy)));
     ok = !(px < 0 || px >= p.W || py < 0 || py >= p.H || camz < 0.0f);  // :110
@@ -155,6 +180,7 @@ __device__ __forceinline__ void integrate_voxel(const TsdfParams& p, const Frame
     camx = __fadd_rn(__fmaf_rn(fr.T[2], wz, __fmaf_rn(fr.T[1], wy, __fmul_rn(fr.T[0], wx))), fr.T[3]);
     camy = __fadd_rn(__fmaf_rn(fr.T[6], wz, __fmaf_rn(fr.T[5], wy, __fmul_rn(fr.T[4], wx))), fr.T[7]);
     camz = __fadd_rn(__fmaf_rn(fr.T[10], wz, __fmaf_rn(fr.T[9], wy, __fmul_rn(fr.T[8], wx))), fr.T[11]);
+    if ((p.variant & 2) && quick_reject(fr, camx, camy, camz, zfar, (float)p.W, (float)p.H)) return;
     const float rx = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(camx, fr.fx), camz), fr.cx));
     const float ry = rintf(__fadd_rn(__fdiv_rn(__fmul_rn(camy, fr.fy), camz), fr.cy));
     ok = (rx >= 0.0f) && (rx < (float)p.W) && (ry >= 0.0f) && (ry < (float)p.H) && (camz > 0.0f);  // :462
@@ -205,6 +231,7 @@ __device__ __forceinline__ void integrate_voxel(const TsdfParams& p, const Frame
 template <int SEM, bool COLOR>
 __global__ void __launch_bounds__(kTsdfThreads) tsdf_integrate_kernel(const TsdfParams p) {
   __shared__ int s_list[kMaxFramesPerLaunch];
+  __shared__ float s_zmax[kMaxFramesPerLaunch];
   __shared__ int s_wcount[kTsdfThreads / 32];
   __shared__ int s_box[6];
   __shared__ int s_n;
@@ -215,7 +242,9 @@ __global__ void __launch_bounds__(kTsdfThreads) tsdf_integrate_kernel(const Tsdf
   __syncthreads();
   for (int f = tid; f < p.F; f += kTsdfThreads) {
     int lo[3], hi[3];
-    if (frame_tile_box(p, p.frames[f], frame_zmax(p, f), lo, hi)) {
+    const float zm = frame_zmax(p, f);
+    s_zmax[f] = zm;
+    if (frame_tile_box(p, p.frames[f], zm, lo, hi)) {
 #pragma unroll
       for (int a = 0; a < 3; ++a) { atomicMin(&s_box[a], lo[a]); atomicMax(&s_box[3 + a], hi[a]); }
     }
@@ -226,7 +255,8 @@ __global__ void __launch_bounds__(kTsdfThreads) tsdf_integrate_kernel(const Tsdf
   if (nbx <= 0 || nby <= 0 || nbz <= 0) return;
   const int64_t ntiles = (int64_t)nbx * nby * nbz;
 
-  const int lz = tid & 15, ly = (tid >> 4) & 7, lxg = tid >> 7;
+  // warp = 4x4x8 sub-box (x: 4 planes of one x-half, y-half, z-half); 8 consecutive z per row -> whole 32-byte sectors
+  const int lz = (tid & 7) + 8 * (warp & 1), ly = ((tid >> 3) & 3) + 4 * ((warp >> 1) & 1), lxg = warp >> 2;
   for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int tz = bz0 + (int)(t % nbz), ty = by0 + (int)((t / nbz) % nby), tx = bx0 + (int)(t / ((int64_t)nbz * nby));
     // tile box over voxel CENTRES, world space
@@ -241,7 +271,7 @@ __global__ void __launch_bounds__(kTsdfThreads) tsdf_integrate_kernel(const Tsdf
     for (int f0 = 0; f0 < p.F; f0 += kTsdfThreads) {
       const int f = f0 + tid;
       bool keep = false;
-      if (f < p.F) keep = tile_hits_frame(p.frames[f], frame_zmax(p, f), p.trunc, c, h);
+      if (f < p.F) keep = tile_hits_frame(p.frames[f], s_zmax[f], p.trunc, c, h);
       const unsigned m = __ballot_sync(0xffffffffu, keep);
       if (lane == 0) s_wcount[warp] = __popc(m);
       __syncthreads();
@@ -277,16 +307,24 @@ __global__ void __launch_bounds__(kTsdfThreads) tsdf_integrate_kernel(const Tsdf
         if (COLOR) cv[i] = p.color[idx[i]];
       }
     }
+    // this warp's sub-box (voxel centres), for the second-level cull
+    const int sx0 = x0 + 4 * lxg, sy0 = y0 + 4 * ((warp >> 1) & 1), sz0 = z0 + 8 * (warp & 1);
+    const float wc[3] = {p.ox + ((float)(sx0 + p.xoff) + 1.5f) * p.vs, p.oy + ((float)sy0 + 1.5f) * p.vs,
+                         p.oz + ((float)sz0 + 3.5f) * p.vs};
+    const float wh[3] = {1.5f * p.vs, 1.5f * p.vs, 3.5f * p.vs};
     for (int li = 0; li < nlist; ++li) {
       const int f = s_list[li];
       const Frame& fr = p.frames[f];
+      const float zm = s_zmax[f];
+      if ((p.variant & 1) && !tile_hits_frame(fr, zm, p.trunc, wc, wh)) continue;  // warp-uniform
+      const float zfar = (zm + p.trunc) * 1.000001f + 1e-6f;
       const float* depth = p.depth + (int64_t)f * p.H * p.W;
       const float* cimg = COLOR ? p.cimg + (int64_t)f * p.H * p.W : nullptr;
 #pragma unroll
       for (int i = 0; i < kVoxPerThread; ++i) {
         if (inb[i])
-          integrate_voxel<SEM, COLOR>(p, fr, depth, cimg, (float)(p.xoff + x0 + lxg * kVoxPerThread + i), (float)y, (float)z,
-                                      tv[i], wv[i], cv[i], dirty[i]);
+          integrate_voxel<SEM, COLOR>(p, fr, depth, cimg, zfar, (float)(p.xoff + x0 + lxg * kVoxPerThread + i), (float)y,
+                                      (float)z, tv[i], wv[i], cv[i], dirty[i]);
       }
     }
 #pragma unroll
@@ -401,6 +439,10 @@ static int tsdf_launch(d3m_tsdf* h, const float* depth, const float* cimg, int F
   TsdfParams p;
   p.tsdf = h->tsdf; p.weight = h->weight; p.color = h->color;
   p.dx = h->dx; p.dy = h->dy; p.dz = h->dz; p.xoff = h->xoff;
+  {
+    static const int variant = getenv("D3M_TSDF_VARIANT") ? atoi(getenv("D3M_TSDF_VARIANT")) : 0;
+    p.variant = variant;
+  }
   p.ox = h->origin[0]; p.oy = h->origin[1]; p.oz = h->origin[2];
   p.vs = h->vs; p.trunc = h->trunc;
   p.frames = d_frames; p.F = F; p.depth = depth; p.cimg = cimg; p.H = H; p.W = W;

@@ -95,7 +95,7 @@ class _CudaLocalOps:
     """The per-rank kernels (libd3m.so).  Tests substitute an object with the same three methods."""
 
     @staticmethod
-    def forward_partial(coords, origin, voxel_size, feats, KRcam):
+    def forward_partial(coords, origin, voxel_size, feats, KRcam, want_hist=False):
         """-> (out (n,C+1) with RAW mean depth in the last column, count (n,), depth_sums (B,3) float64, state)"""
         L = _lib.lib()
         if not feats.is_cuda:
@@ -108,15 +108,18 @@ class _CudaLocalOps:
         out = torch.empty((N, C + 1), dtype=torch.float32, device=dev)
         count = torch.empty((N,), dtype=torch.float32, device=dev)
         sums = torch.zeros((B, 3), dtype=torch.float64, device=dev)
+        hist = None
+        if want_hist:
+            hist = (torch.empty if N > 0 else torch.zeros)((V, B, H, W), dtype=torch.int32, device=dev)
         ws, ws_bytes = voxel._workspace("f", (max(N, 1), B, V, C), dev)
         if N > 0:
             with voxel._on_device(dev):
                 rc = L.d3m_back_project_fwd_partial(coords.data_ptr(), voxel._COORD_KIND[coords.dtype], N,
                                                     origin.data_ptr(), B, float(voxel_size), nhwc.data_ptr(), V, C, H, W,
-                                                    KRcam.data_ptr(), out.data_ptr(), count.data_ptr(), sums.data_ptr(),
-                                                    ws.data_ptr(), ws_bytes, voxel._stream(dev))
+                                                    KRcam.data_ptr(), out.data_ptr(), count.data_ptr(), voxel._ptr(hist),
+                                                    sums.data_ptr(), ws.data_ptr(), ws_bytes, voxel._stream(dev))
             _lib.check(rc, "d3m_back_project_fwd_partial")
-        return out, count, sums, (ws, ws_bytes, tuple(nhwc.shape), coords, origin, KRcam)
+        return out, count, sums, (ws, ws_bytes, tuple(nhwc.shape), coords, origin, KRcam, hist)
 
     @staticmethod
     def forward_finish(out, sums, state):
@@ -133,15 +136,16 @@ class _CudaLocalOps:
 
     @staticmethod
     def backward(state, voxel_size, grad_out, count):
-        _, _, nhwc_shape, coords, origin, KRcam = state
+        _, _, nhwc_shape, coords, origin, KRcam, hist = state
         return voxel.back_project_backward(coords, origin, voxel_size, nhwc_shape, KRcam, grad_out, nchw=True,
-                                           count=count)
+                                           count=count, cell_hist=hist)
 
 
 class _BackProjectVoxelSharded(torch.autograd.Function):
     @staticmethod
     def forward(ctx, feats, coords_local, origin, voxel_size, KRcam, group, ops):
-        out, count, sums, state = ops.forward_partial(coords_local, origin, voxel_size, feats, KRcam)
+        out, count, sums, state = ops.forward_partial(coords_local, origin, voxel_size, feats, KRcam,
+                                                      want_hist=ctx.needs_input_grad[0])
         if _world(group)[1] > 1:
             dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)  # 3 fp64 scalars per fragment
         out = ops.forward_finish(out, sums, state)

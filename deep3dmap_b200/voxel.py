@@ -100,8 +100,9 @@ def _prep_small(coords, origin, KRcam, device):
     return coords, _as(origin, device, torch.float32), _as(KRcam, device, torch.float32)
 
 
-def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam):
-    """Kernel-level forward on channels-last maps (V,B,H,W,C).  Returns (volume (N,C+1), count (N,))."""
+def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam, cell_hist=False):
+    """Kernel-level forward on channels-last maps (V,B,H,W,C).  Returns (volume (N,C+1), count (N,)) and, with
+    cell_hist=True, additionally the (V,B,H,W) int32 per-cell sample histogram the backward pass starts from."""
     L = _lib.lib()
     dev = feats_nhwc.device
     V, B, H, W, C = feats_nhwc.shape
@@ -110,20 +111,25 @@ def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam):
         raise ValueError("origin must be (B,3) and KRcam (V,B,4,4) for feats (V,B,C,H,W)")
     out = torch.empty((N, C + 1), dtype=torch.float32, device=dev)
     count = torch.empty((N,), dtype=torch.float32, device=dev)
-    if N == 0:
-        return out, count
-    ws, ws_bytes = _workspace("f", (N, B, V, C), dev)
-    with _on_device(dev):
-        rc = L.d3m_back_project_fwd(coords.data_ptr(), _COORD_KIND[coords.dtype], N, origin.data_ptr(), B,
-                                    float(voxel_size), feats_nhwc.data_ptr(), V, C, H, W, KRcam.data_ptr(),
-                                    out.data_ptr(), count.data_ptr(), ws.data_ptr(), ws_bytes, _stream(dev))
-    _lib.check(rc, "d3m_back_project_fwd")
-    return out, count
+    hist = None
+    if cell_hist:
+        hist = (torch.empty if N > 0 else torch.zeros)((V, B, H, W), dtype=torch.int32, device=dev)
+    if N > 0:
+        ws, ws_bytes = _workspace("f", (N, B, V, C), dev)
+        with _on_device(dev):
+            rc = L.d3m_back_project_fwd(coords.data_ptr(), _COORD_KIND[coords.dtype], N, origin.data_ptr(), B,
+                                        float(voxel_size), feats_nhwc.data_ptr(), V, C, H, W, KRcam.data_ptr(),
+                                        out.data_ptr(), count.data_ptr(), _ptr(hist), ws.data_ptr(), ws_bytes,
+                                        _stream(dev))
+        _lib.check(rc, "d3m_back_project_fwd")
+    return (out, count, hist) if cell_hist else (out, count)
 
 
-def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, grad_out, nchw=False, count=None):
+def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, grad_out, nchw=False, count=None,
+                          cell_hist=None):
     """Kernel-level backward: grad_out (N,C+1) -> grad of the maps, channels-last (V,B,H,W,C) or, with
-    nchw=True, in the reference layout (V,B,C,H,W) written directly by the gather kernel."""
+    nchw=True, in the reference layout (V,B,C,H,W) written directly by the gather kernel.  `count` / `cell_hist`
+    from the forward pass of the same inputs are optional shortcuts (recomputed when None; same bits either way)."""
     L = _lib.lib()
     dev = grad_out.device
     V, B, H, W, C = feats_shape_nhwc
@@ -134,8 +140,8 @@ def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, g
     ws, ws_bytes = _workspace("b", (N, B, V, C, H, W), dev)
     with _on_device(dev):
         rc = L.d3m_back_project_bwd(_ptr(coords), _COORD_KIND[coords.dtype], N, _ptr(origin), B, float(voxel_size),
-                                    V, C, H, W, _ptr(KRcam), _ptr(grad_out), _ptr(count), grad.data_ptr(), 1 if nchw else 0,
-                                    ws.data_ptr(), ws_bytes, _stream(dev))
+                                    V, C, H, W, _ptr(KRcam), _ptr(grad_out), _ptr(count), _ptr(cell_hist), grad.data_ptr(),
+                                    1 if nchw else 0, ws.data_ptr(), ws_bytes, _stream(dev))
     _lib.check(rc, "d3m_back_project_bwd")
     return grad
 
@@ -150,8 +156,13 @@ class _BackProject(torch.autograd.Function):
         dev = feats.device
         coords, origin, KRcam = _prep_small(coords, origin, KRcam, dev)
         nhwc = feats_to_channels_last(feats)
-        out, count = back_project_forward(coords, origin, voxel_size, nhwc, KRcam)
-        ctx.save_for_backward(coords, origin, KRcam, count)
+        if ctx.needs_input_grad[0]:
+            # backward will follow: let the forward pass, which projects every voxel anyway, histogram the samples
+            out, count, hist = back_project_forward(coords, origin, voxel_size, nhwc, KRcam, cell_hist=True)
+            ctx.save_for_backward(coords, origin, KRcam, count, hist)
+        else:
+            out, count = back_project_forward(coords, origin, voxel_size, nhwc, KRcam)
+            ctx.save_for_backward(coords, origin, KRcam, count)
         ctx.voxel_size = float(voxel_size)
         ctx.nhwc_shape = tuple(nhwc.shape)
         ctx.mark_non_differentiable(count)
@@ -160,16 +171,16 @@ class _BackProject(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_vol, grad_count):
-        coords, origin, KRcam, count = ctx.saved_tensors
-        if not ctx.needs_input_grad[0]:
+        if not ctx.needs_input_grad[0] or grad_vol is None:
             return None, None, None, None, None
-        if grad_vol is None:
-            return None, None, None, None, None
+        coords, origin, KRcam, count, hist = ctx.saved_tensors
         g = grad_vol if (grad_vol.is_contiguous() and grad_vol.dtype == torch.float32) else grad_vol.contiguous().float()
         if GRAD_LAYOUT == "view":
-            grad = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g, count=count).permute(0, 1, 4, 2, 3)
+            grad = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g, count=count,
+                                         cell_hist=hist).permute(0, 1, 4, 2, 3)
         else:
-            grad = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g, nchw=True, count=count)
+            grad = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g, nchw=True, count=count,
+                                         cell_hist=hist)
         return grad, None, None, None, None
 
 

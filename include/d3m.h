@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 100
+#define D3M_VERSION 101
 
 enum {
   D3M_OK = 0,
@@ -74,12 +74,16 @@ int d3m_feats_nhwc_to_nchw(const float* src, float* dst, int64_t n_maps, int C, 
  *   out         (N,C+1) float32: view-mean features | normalised mean depth   (written for every row;
  *               rows whose batch index is outside [0,B) are zero, as in the reference)
  *   count       (N,) float32: number of views that see the voxel (bit-exact contract)
+ *   cell_hist   NULL, or (V,B,H,W) int32 (16-byte aligned): receives the number of valid samples per bilinear cell
+ *               (v,b,y0,x0).  It is the first step of the deterministic backward; producing it here, where every
+ *               voxel is projected anyway, saves the backward one full projection pass.  Pass it to
+ *               d3m_back_project_bwd for the SAME coords / KRcam (the autograd wrapper does when feats needs grad).
  * workspace: d3m_back_project_fwd_workspace(N,B,V,C) bytes, 256-byte aligned.
  * ------------------------------------------------------------------------------------------- */
 size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C);
 int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                          float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                         const float* KRcam, float* out, float* count, void* workspace,
+                         const float* KRcam, float* out, float* count, int* cell_hist, void* workspace,
                          size_t workspace_bytes, void* stream);
 
 /* Voxel-range sharding (BASELINE config 5): every rank runs the gather on its contiguous slice of the coordinate
@@ -92,7 +96,7 @@ int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const f
  *             must be the buffer handed to _partial for the same slice, untouched in between. */
 int d3m_back_project_fwd_partial(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                                  float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                                 const float* KRcam, float* out, float* count, double* depth_sums,
+                                 const float* KRcam, float* out, float* count, int* cell_hist, double* depth_sums,
                                  void* workspace, size_t workspace_bytes, void* stream);
 int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sums, float* out, void* workspace,
                                 size_t workspace_bytes, void* stream);
@@ -101,18 +105,21 @@ int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sum
  * back_project backward w.r.t. feats  (replaces autograd through back_project.py:55-73:
  * div backward, mask, grid_sampler_2d_backward).  Deterministic: samples are binned per texel with
  * integer atomics only, each bin is ordered by voxel index, and every texel is accumulated by one
- * lane group in a fixed order -- no floating-point atomics anywhere.
+ * lane group in a fixed order -- no floating-point atomics anywhere.  The result is a pure function of the inputs
+ * (bit-identical run to run and independent of whether count / cell_hist were handed over).
  *   grad_out         (N,C+1) float32 (the depth column carries no gradient to feats)
  *   count            (N,) float32 as returned by d3m_back_project_fwd for the same inputs, or NULL
  *                    (then the view counts are recomputed by one extra kernel)
+ *   cell_hist        (V,B,H,W) int32 as produced by d3m_back_project_fwd for the same inputs (read-only here, so
+ *                    backward may run more than once), or NULL (then one extra projection pass rebuilds it)
  *   grad_feats       float32, fully overwritten; (V,B,H,W,C) when grad_nchw == 0, the reference's
  *                    (V,B,C,H,W) when grad_nchw != 0 (the gather kernel then stores channel-strided)
  * ------------------------------------------------------------------------------------------- */
 size_t d3m_back_project_bwd_workspace(int64_t N, int B, int V, int C, int H, int W);
 int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                          float voxel_size, int V, int C, int H, int W, const float* KRcam,
-                         const float* grad_out, const float* count, float* grad_feats, int grad_nchw,
-                         void* workspace, size_t workspace_bytes, void* stream);
+                         const float* grad_out, const float* count, const int* cell_hist, float* grad_feats,
+                         int grad_nchw, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * TSDF fusion  (replaces TSDFVolume, tsdf_volume.py:10-307, and TSDFVolumeTorch :485-574)

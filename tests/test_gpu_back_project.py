@@ -182,6 +182,28 @@ def test_backward_without_forward_count_recomputes_it():
     assert torch.equal(g1, g2)
     assert torch.equal(g1.permute(0, 1, 4, 2, 3), g3)
     assert torch.equal(voxel.feats_to_nchw(g1), g3)
+    # the forward pass can also hand over the per-cell sample histogram (what the autograd wrapper does)
+    vol2, cnt2, hist = voxel.back_project_forward(coords, origin, 0.04, nhwc, KR, cell_hist=True)
+    assert torch.equal(vol, vol2) and torch.equal(cnt, cnt2)
+    assert int(hist.sum()) == int(cnt.sum()) and hist.dtype == torch.int32
+    g4 = voxel.back_project_backward(coords, origin, 0.04, shape, KR, go, count=cnt, cell_hist=hist)
+    g5 = voxel.back_project_backward(coords, origin, 0.04, shape, KR, go, count=cnt, cell_hist=hist)  # hist is read-only
+    assert torch.equal(g1, g4) and torch.equal(g1, g5)
+
+
+def test_backward_twice_with_retain_graph():
+    from deep3dmap_b200 import back_project
+    inp = cases.bp_level(0, 4000, np.float32)
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(a).to(dev)
+    feats = t(inp["feats"]).requires_grad_(True)
+    vol, _ = back_project(t(inp["coords"]), t(inp["origin"]), 0.04, feats, t(inp["KRcam"]))
+    go = t(inp["grad_out"])
+    vol.backward(go, retain_graph=True)
+    g1 = feats.grad.clone()
+    feats.grad = None
+    vol.backward(go)
+    assert torch.equal(g1, feats.grad)
 
 
 def test_heavy_collisions_large_cells():

@@ -22,7 +22,7 @@ class OracleLocalOps:
     """Same three methods as shard._CudaLocalOps, computed by the CPU oracle on CPU tensors."""
 
     @staticmethod
-    def forward_partial(coords, origin, voxel_size, feats, KRcam):
+    def forward_partial(coords, origin, voxel_size, feats, KRcam, want_hist=False):
         f = feats.detach().numpy()
         B, C = f.shape[1], f.shape[2]
         c, o, k = coords.numpy(), origin.numpy(), KRcam.numpy()

@@ -12,10 +12,11 @@ echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps
 echo "== ncu launch list (bp step)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_bp.csv python bench.py --profile-step bp --steps 2 --warmup 3 --no-graph > $OUT/ncu_bp.log 2>&1 ; echo "rc=$?"
 echo "== ncu launch list (dense + tsdf)"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file $OUT/launches_dense.csv python bench.py --profile-step dense --steps 1 --warmup 3 --no-graph > $OUT/ncu_dense.log 2>&1 ; echo "rc=$?"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:tsdf -c 60 --csv --log-file $OUT/launches_tsdf.csv python bench.py --profile-step tsdf --steps 1 --warmup 3 --no-graph > $OUT/ncu_tsdf.log 2>&1 ; echo "rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches_dense.csv python bench.py --profile-step dense --steps 1 --warmup 3 --no-graph > $OUT/ncu_dense.log 2>&1 ; echo "rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches_tsdf.csv python bench.py --profile-step tsdf --steps 1 --warmup 3 --no-graph > $OUT/ncu_tsdf.log 2>&1 ; echo "rc=$?"
 echo "== ncu full: dense level-2 fwd + bwd kernels"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'bp_' -s 120 -c 8 -o $OUT/prof_dense -f python bench.py --profile-step dense --steps 1 --warmup 3 --no-graph > $OUT/ncu_full_dense.log 2>&1 ; echo "rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o $OUT/prof_dense -f python bench.py --profile-step dense --steps 1 --warmup 3 --no-graph > $OUT/ncu_full_dense.log 2>&1 ; echo "rc=$?"
 echo "== ncu full: tsdf"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:tsdf_integrate -c 3 -o $OUT/prof_tsdf -f python bench.py --profile-step tsdf --steps 1 --warmup 3 --no-graph > $OUT/ncu_full_tsdf.log 2>&1 ; echo "rc=$?"
+timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tsdf_integrate -c 2 -o $OUT/prof_tsdf -f python bench.py --profile-step tsdf --steps 1 --warmup 3 --no-graph > $OUT/ncu_full_tsdf.log 2>&1 ; echo "rc=$?"
 ls -la $OUT
+echo "== tsdf host profile" ; timeout 300 python tools/tsdf_host_profile.py > $OUT/tsdf_host_profile.txt 2>&1 ; cat $OUT/tsdf_host_profile.txt
