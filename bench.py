@@ -328,7 +328,8 @@ def run_ours(args, rank, world, local_rank):
 
     def step_e2e():
         main = torch.cuda.current_stream()
-        for hp, st in zip(pin, e2e_streams):
+        # largest level first: its D2H then overlaps the H2D of the smaller ones (copy engines are FIFO per direction)
+        for hp, st in reversed(list(zip(pin, e2e_streams))):
             st.wait_stream(main)
             with torch.cuda.stream(st):
                 c = hp["coords"].to(dev, non_blocking=True)
@@ -382,6 +383,10 @@ def run_ours(args, rank, world, local_rank):
                     e["n"] += v["n"]; e["ms"] += v["ms"]
             per_level.append(acc)
         prof = per_level
+
+    # ---- multi-rank legs (every rank takes part): BASELINE configs[3] and configs[4] ---------------------
+    batched = bench_batched_fragments(torch, dist, dev, back_project, levels, flush_buf, rank, world, peak_gbs)
+    scene = bench_large_scene(torch, dist, dev, flush_buf, rank, world)
 
     # ---- large-volume leg: dense 96^3 level-2 call (BASELINE configs[0] shape, N = 884,736, 7.96 M samples) ----
     dense = None
@@ -468,11 +473,149 @@ def run_ours(args, rank, world, local_rank):
                          "sample": "5 full steps of the same fragment on the host (OpenMP C port of the reference "
                                    "algorithm; %.1f ms/step)" % (cpu_sec * 1e3)},
         "dense_level2": dense,
+        "batched_fragments": batched,
+        "large_scene": scene,
         "tsdf": tsdf,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def _max_over_ranks(torch, dist, dev, ms, world):
+    if world == 1:
+        return ms
+    t = torch.tensor([ms], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t[0])
+
+
+def bench_batched_fragments(torch, dist, dev, back_project, levels, flush_buf, rank, world, peak_gbs, n_fragments=64):
+    """BASELINE configs[3]: 64 fragments x 9 views, fragment-parallel.  Every rank owns 64/world fragments and issues ONE
+    back_project call per level with all of them (B = 64/world); there is no data-path collective.  Geometry: the sparse
+    coordinate sets of the headline fragment, re-used for every fragment (its cameras move with its origin); features
+    and output gradients are N(0,1) generated on the device (this leg measures throughput, parity is covered elsewhere)."""
+    from deep3dmap_b200 import shard
+    mine = shard.fragments_of_rank(n_fragments, rank, world)
+    Bl = len(mine)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(4242 + rank)
+    calls, samples, alg = [], 0, 0
+    for lv, inp in enumerate(levels):
+        V, _, C, H, W = inp["feats"].shape
+        n1 = inp["coords"].shape[0]
+        c1 = torch.from_numpy(inp["coords"]).to(dev)
+        coords = c1.repeat(Bl, 1)
+        coords[:, 0] = torch.arange(Bl, device=dev).repeat_interleave(n1).to(coords.dtype)
+        origin = np.zeros((Bl, 3), np.float32)
+        KR = np.zeros((V, Bl, 4, 4), np.float32)
+        K = synth.scaled_K(synth.LEVELS[lv]["scale"])
+        for j, f in enumerate(mine):
+            off = (3.84 * (f % 8), 3.84 * (f // 8), 0.0)
+            origin[j] = off
+            R, c = synth.fragment_cameras(V, offset=off)
+            KR[:, j] = synth.krcam_from(R, c, K)
+        feats = torch.randn((V, Bl, C, H, W), device=dev, generator=gen).requires_grad_(True)
+        go = torch.randn((n1 * Bl, C + 1), device=dev, generator=gen)
+        calls.append((coords, torch.from_numpy(origin).to(dev), inp["voxel_size"], feats, torch.from_numpy(KR).to(dev), go))
+        samples += n1 * Bl * V
+
+    def step():
+        cnts = []
+        for coords, origin, vs, feats, KR, go in calls:
+            feats.grad = None
+            vol, cnt = back_project(coords, origin, vs, feats, KR)
+            vol.backward(go)
+            cnts.append(cnt)
+        return cnts
+
+    for _ in range(2):
+        cnts = step()
+    torch.cuda.synchronize()
+    for (coords, _, _, feats, _, _), cnt, inp in zip(calls, cnts, levels):
+        V, B, C, H, W = feats.shape
+        S = int(cnt.sum().item())
+        cb = coords.element_size() * 4
+        N = coords.shape[0]
+        alg += 2 * (N * (cb + 4 * (C + 1) + 4) + 16 * C * S) + 64 * V * B + 4 * V * B * C * H * W
+    ts = []
+    for _ in range(5):
+        flush_buf.fill_(1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = _max_over_ranks(torch, dist, dev, float(np.mean(ts)), world)
+    tot = torch.tensor([float(samples), float(alg)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot)
+    del calls
+    torch.cuda.empty_cache()
+    return {"fragments": n_fragments, "fragments_per_rank": Bl, "samples_per_step": int(tot[0].item()),
+            "ms_per_step": ms, "samples_per_s": float(tot[0].item()) / (ms * 1e-3), "scaling": "strong",
+            "algorithmic_bytes_per_step": int(tot[1].item()),
+            "achieved_GBs_per_gpu": float(tot[1].item()) / world / (ms * 1e-3) / 1e9,
+            "frac_of_measured_hbm_peak_per_gpu": float(tot[1].item()) / world / (ms * 1e-3) / 1e9 / peak_gbs,
+            "collectives": "none (fragment-parallel)"}
+
+
+def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
+    """BASELINE configs[4]: 1024^3 index space @ 4 cm, 64 views, finest level (C=24, 120x160 maps), wall-shell sparse set
+    (~1 % occupancy), voxel-range sharded: feats / KRcam replicated, each rank gathers its contiguous slice; per step
+    one all-reduce of 3 fp64 scalars (depth normalisation), one all-reduce of grad_feats (118 MB) and one all-gather of
+    the per-shard view counts (the occupancy slab the next coarse-to-fine level needs)."""
+    from deep3dmap_b200 import shard
+    V, lv = 64, 2
+    L = synth.LEVELS[lv]
+    coords_all = synth.large_scene_coords(dtype=np.int32)
+    N = coords_all.shape[0]
+    b0, b1 = shard.voxel_range(N, rank, world)
+    coords = torch.from_numpy(np.ascontiguousarray(coords_all[b0:b1])).to(dev)
+    del coords_all
+    R, c = synth.large_scene_cameras(V)
+    KR = torch.from_numpy(synth.krcam_from(R, c, synth.scaled_K(L["scale"]))[:, None].copy()).to(dev)
+    origin = torch.zeros((1, 3), device=dev)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(777)  # same seed on every rank: replicated feature maps
+    feats = torch.randn((V, 1, L["C"], L["H"], L["W"]), device=dev, generator=gen).requires_grad_(True)
+    gen.manual_seed(778 + rank)
+    go = torch.randn((b1 - b0, L["C"] + 1), device=dev, generator=gen)
+    sizes = [shard.voxel_range(N, r, world)[1] - shard.voxel_range(N, r, world)[0] for r in range(world)]
+
+    def step():
+        feats.grad = None
+        vol, cnt = shard.back_project_voxel_sharded(coords, origin, synth.VOXEL_SIZE, feats, KR)
+        vol.backward(go)
+        return shard.all_gather_rows(cnt, sizes=sizes), cnt
+
+    for _ in range(2):
+        full_cnt, cnt = step()
+    torch.cuda.synchronize()
+    S = torch.tensor([float(cnt.sum().item())], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(S)
+    ts = []
+    for _ in range(3):
+        flush_buf.fill_(1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); step(); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = _max_over_ranks(torch, dist, dev, float(np.mean(ts)), world)
+    res = {"index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": int(b1 - b0),
+           "samples_per_step": int(N) * V, "valid_samples": int(S[0].item()), "ms_per_step": ms,
+           "samples_per_s": N * V / (ms * 1e-3), "scaling": "strong",
+           "collectives": "all_reduce(3 fp64 per fragment) + all_reduce(grad_feats %.0f MB) + all_gather(count, %d B/voxel)"
+                          % (feats.numel() * 4 / 1e6, 4), "full_count_rows": int(full_cnt.shape[0])}
+    del coords, feats, go
+    torch.cuda.empty_cache()
+    return res
 
 
 def bench_dense_l2(torch, dev, _lib, back_project, flush_buf, peak_gbs, steps, profile_only=False):

@@ -19,6 +19,8 @@
 //           shared memory; after one barrier every texel adds its four partials in the fixed order
 //           nw(y,x) + ne(y,x-1) + sw(y-1,x) + se(y-1,x-1) and is stored once.  (A texel-centric walk reads every
 //           row four times and was bound by L2->SM load latency.)
+#include <stdlib.h>
+
 #include "d3m_common.cuh"
 
 namespace d3m {
@@ -78,14 +80,15 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_count_kernel(const BwdP
   cnt_out[n] = (float)cnt;
 }
 
-// One thread per (voxel, view) pair: blockIdx.y = view.  Short dependency chains and N*V-way parallelism instead of
+// One thread per (voxel, group of kViewsPerThread views): blockIdx.y = view group.  Short dependency chains and N*V-way parallelism instead of
 // a 9-deep serial loop per voxel (these passes are latency-bound at fragment size).
 //   FILL = false: histogram the valid samples per bilinear cell (integer RED).  Skipped entirely when the forward
 //                 pass already produced the histogram (d3m_back_project_fwd(..., cell_hist)).
 //   FILL = true : claim the cell's next entry position (one integer atomic on the cursor), store {n, fx, fy, cell}.
+constexpr int kViewsPerThread = 3;  // independent atomics in flight per thread (the pass is latency-bound on them)
 template <int KIND, bool FILL>
 __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const BwdParams p) {
-  const int v = blockIdx.y;
+  const int v0 = blockIdx.y * kViewsPerThread;
   const int64_t n = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
   if (n >= p.N) return;
   float cx, cy, cz;
@@ -94,16 +97,35 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const Bwd
   float gx, gy, gz;
   const float* o = p.origin + 3 * b;
   voxel_world(cx, cy, cz, p.vs, __ldg(o), __ldg(o + 1), __ldg(o + 2), gx, gy, gz);
-  float4 r0, r1, r2;
-  load_krcam(p.KR, v, p.B, b, r0, r1, r2);
-  const Sample s = project(gx, gy, gz, r0, r1, r2, (float)(p.W - 1), (float)(p.H - 1));
-  if (!s.valid) return;
-  const int key = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
+  int key[kViewsPerThread];
+  float fx[kViewsPerThread], fy[kViewsPerThread];
+  bool ok[kViewsPerThread];
+#pragma unroll
+  for (int j = 0; j < kViewsPerThread; ++j) {
+    const int v = v0 + j;
+    ok[j] = v < p.V;
+    key[j] = 0; fx[j] = 0.f; fy[j] = 0.f;
+    if (ok[j]) {
+      float4 r0, r1, r2;
+      load_krcam(p.KR, v, p.B, b, r0, r1, r2);
+      const Sample s = project(gx, gy, gz, r0, r1, r2, (float)(p.W - 1), (float)(p.H - 1));
+      ok[j] = s.valid;
+      key[j] = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
+      fx[j] = s.fx; fy[j] = s.fy;
+    }
+  }
   if (!FILL) {
-    atomicAdd(p.bin_cnt + key, 1);
+#pragma unroll
+    for (int j = 0; j < kViewsPerThread; ++j)
+      if (ok[j]) atomicAdd(p.bin_cnt + key[j], 1);
   } else {
-    const int pos = atomicAdd(p.bin_cursor + key, 1);  // claim order is arbitrary; `order` fixes it
-    p.entries[pos] = make_int4((int)n, __float_as_int(s.fx), __float_as_int(s.fy), key);
+    int pos[kViewsPerThread];
+#pragma unroll
+    for (int j = 0; j < kViewsPerThread; ++j)   // claim order is arbitrary; `order` fixes it
+      pos[j] = ok[j] ? atomicAdd(p.bin_cursor + key[j], 1) : 0;
+#pragma unroll
+    for (int j = 0; j < kViewsPerThread; ++j)
+      if (ok[j]) p.entries[pos[j]] = make_int4((int)n, __float_as_int(fx[j]), __float_as_int(fy[j]), key[j]);
   }
 }
 
@@ -280,12 +302,17 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_tile_kernel(c
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
 
   // ---- phase 1: cells -> four corner partial sums each ------------------------------------------
+  // (row, col) of this group's cell inside the (CH x CW) cell window, advanced by kGroups cells per round
+  const int step_r = kGroups / CW, step_c = kGroups - step_r * CW;
+  int crow = gid / CW, ccol = gid - crow * CW;
   for (int c0 = 0; c0 < ncell; c0 += kGroups) {
     const int cl = c0 + gid;
     const bool slot = gact && cl < ncell;
+    const int cy = y0 - 1 + crow, cx = x0 - 1 + ccol;
+    crow += step_r; ccol += step_c;
+    if (ccol >= CW) { ccol -= CW; ++crow; }
     int s = 0, e = 0;
     if (slot) {
-      const int cy = y0 - 1 + cl / CW, cx = x0 - 1 + cl % CW;
       if (cy >= 0 && cx >= 0 && cy < p.H && cx < p.W) {
         const int64_t cell = map_base + (int64_t)cy * p.W + cx;
         s = __ldg(p.bin_start + cell);
@@ -328,14 +355,16 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_tile_kernel(c
 #pragma unroll
         for (int i = 0; i < R; ++i) {
           const float4 q = rows[j][i];
-          anw[i].x = __fadd_rn(anw[i].x, __fmul_rn(nw, q.x)); anw[i].y = __fadd_rn(anw[i].y, __fmul_rn(nw, q.y));
-          anw[i].z = __fadd_rn(anw[i].z, __fmul_rn(nw, q.z)); anw[i].w = __fadd_rn(anw[i].w, __fmul_rn(nw, q.w));
-          ane[i].x = __fadd_rn(ane[i].x, __fmul_rn(ne, q.x)); ane[i].y = __fadd_rn(ane[i].y, __fmul_rn(ne, q.y));
-          ane[i].z = __fadd_rn(ane[i].z, __fmul_rn(ne, q.z)); ane[i].w = __fadd_rn(ane[i].w, __fmul_rn(ne, q.w));
-          asw[i].x = __fadd_rn(asw[i].x, __fmul_rn(sw, q.x)); asw[i].y = __fadd_rn(asw[i].y, __fmul_rn(sw, q.y));
-          asw[i].z = __fadd_rn(asw[i].z, __fmul_rn(sw, q.z)); asw[i].w = __fadd_rn(asw[i].w, __fmul_rn(sw, q.w));
-          ase[i].x = __fadd_rn(ase[i].x, __fmul_rn(se, q.x)); ase[i].y = __fadd_rn(ase[i].y, __fmul_rn(se, q.y));
-          ase[i].z = __fadd_rn(ase[i].z, __fmul_rn(se, q.z)); ase[i].w = __fadd_rn(ase[i].w, __fmul_rn(se, q.w));
+          // fused multiply-add: one rounding per contribution (aten rounds the product first; the difference is
+          // <= 0.5 ulp per term, inside the 1e-5 gradient tolerance) and half the FP instructions of mul + add
+          anw[i].x = __fmaf_rn(nw, q.x, anw[i].x); anw[i].y = __fmaf_rn(nw, q.y, anw[i].y);
+          anw[i].z = __fmaf_rn(nw, q.z, anw[i].z); anw[i].w = __fmaf_rn(nw, q.w, anw[i].w);
+          ane[i].x = __fmaf_rn(ne, q.x, ane[i].x); ane[i].y = __fmaf_rn(ne, q.y, ane[i].y);
+          ane[i].z = __fmaf_rn(ne, q.z, ane[i].z); ane[i].w = __fmaf_rn(ne, q.w, ane[i].w);
+          asw[i].x = __fmaf_rn(sw, q.x, asw[i].x); asw[i].y = __fmaf_rn(sw, q.y, asw[i].y);
+          asw[i].z = __fmaf_rn(sw, q.z, asw[i].z); asw[i].w = __fmaf_rn(sw, q.w, asw[i].w);
+          ase[i].x = __fmaf_rn(se, q.x, ase[i].x); ase[i].y = __fmaf_rn(se, q.y, ase[i].y);
+          ase[i].z = __fmaf_rn(se, q.z, ase[i].z); ase[i].w = __fmaf_rn(se, q.w, ase[i].w);
         }
       }
     }
@@ -481,15 +510,21 @@ static gather_kernel_t pick_gather_kernel(int C) {
 }
 
 // texel tile of the gather kernel: the largest of a fixed ladder whose 4 x (TX+1)(TY+1) x C floats fit the budget
-static void pick_gather_tile(int C, int H, int W, int& TX, int& TY, size_t& smem) {
+// Measured on B200 (profiles/r01_bp_gather_tile.txt): small tiles win -- more CTAs per SM hide the dependent
+// bin_start -> entry -> row load chain better than a smaller halo helps -- down to 8x4 texels; C = 24 -> 8x8 (31 KB),
+// C = 40 -> 8x4 (29 KB), C = 80 -> 8x4 (58 KB).
+static void pick_gather_tile(int C, int& TX, int& TY, size_t& smem) {
   static const int ladder[][2] = {{16, 8}, {8, 8}, {8, 4}, {4, 4}, {2, 2}, {1, 1}};
-  const size_t budget = 64 * 1024;
-  for (auto& t : ladder) {
-    TX = t[0]; TY = t[1];
-    smem = (size_t)16 * C * (TX + 1) * (TY + 1);
-    if (smem <= budget) break;
+  static const int env_kb = getenv("D3M_GATHER_SMEM_KB") ? atoi(getenv("D3M_GATHER_SMEM_KB")) : 0;  // tuning aid
+  for (int pass = 0; pass < 2; ++pass) {
+    const size_t budget = env_kb ? (size_t)env_kb * 1024 : (pass == 0 ? 32 * 1024 : 64 * 1024);
+    for (auto& t : ladder) {
+      TX = t[0]; TY = t[1];
+      smem = (size_t)16 * C * (TX + 1) * (TY + 1);
+      if (smem <= budget) break;
+    }
+    if (env_kb || TX * TY >= 32) break;  // never below 8x4 texels if 64 KB can hold it
   }
-  (void)H; (void)W;
 }
 
 template <int KIND>
@@ -507,7 +542,7 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
   D3M_CUDA_CHECK(cudaGetLastError());
   if (!have_hist) {
     LaunchScope ls("bp_bwd_hist", stream);
-    bp_bwd_sample_kernel<KIND, false><<<dim3(vox_ctas, p.V), kSampleThreads, 0, stream>>>(p);
+    bp_bwd_sample_kernel<KIND, false><<<dim3(vox_ctas, (p.V + kViewsPerThread - 1) / kViewsPerThread), kSampleThreads, 0, stream>>>(p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
@@ -520,7 +555,7 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
   D3M_CUDA_CHECK(cudaGetLastError());
   {
     LaunchScope ls("bp_bwd_fill", stream);
-    bp_bwd_sample_kernel<KIND, true><<<dim3(vox_ctas, p.V), kSampleThreads, 0, stream>>>(p);
+    bp_bwd_sample_kernel<KIND, true><<<dim3(vox_ctas, (p.V + kViewsPerThread - 1) / kViewsPerThread), kSampleThreads, 0, stream>>>(p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
@@ -535,7 +570,7 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
   if (k) {
     int TX, TY;
     size_t smem;
-    pick_gather_tile(p.C, p.H, p.W, TX, TY, smem);
+    pick_gather_tile(p.C, TX, TY, smem);
     const int tiles_x = (p.W + TX - 1) / TX, tiles_y = (p.H + TY - 1) / TY;
     const int64_t tiles = (int64_t)p.V * p.B * tiles_x * tiles_y;
     D3M_REQUIRE(tiles < (1ll << 31), D3M_ERR_ARG, "back_project backward: too many gather tiles");

@@ -321,7 +321,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const Fw
 // fp64 (relative error ~1e-15 here), so one pass over the compact z array suffices.
 // ------------------------------------------------------------------------------------------------
 constexpr int kStatsThreads = 256;
-constexpr int kStatsChunk = 4096;
+constexpr int kStatsChunk = 2048;
 constexpr int kStatsMaxChunks = 2048;
 
 struct StatsParams {
@@ -366,24 +366,45 @@ __global__ void __launch_bounds__(kStatsThreads) bp_stats_kernel(const StatsPara
   const int64_t i0 = (int64_t)blockIdx.x * p.chunk, i1 = min(p.N, i0 + p.chunk);
   if (tid == 0) { s_bmin = 0x7fffffff; s_bmax = -1; }
   __syncthreads();
-  int bmin = 0x7fffffff, bmax = -1;
-  for (int64_t i = i0 + tid; i < i1; i += kStatsThreads) {
-    const int b = p.bidx[i];
-    if (b >= 0) { bmin = min(bmin, b); bmax = max(bmax, b); }
+  int bmin = 0, bmax = 0;
+  if (p.B > 1) {  // which fragments occur in this chunk (usually one)
+    bmin = 0x7fffffff; bmax = -1;
+    for (int64_t i = i0 + 4 * tid; i < i1; i += 4 * kStatsThreads) {  // i0 and chunk are multiples of 4
+      int bb[4] = {-1, -1, -1, -1};
+      if (i + 4 <= i1) {
+        const int4 t = *reinterpret_cast<const int4*>(p.bidx + i);
+        bb[0] = t.x; bb[1] = t.y; bb[2] = t.z; bb[3] = t.w;
+      } else {
+        for (int k = 0; k < 4; ++k) if (i + k < i1) bb[k] = p.bidx[i + k];
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) if (bb[k] >= 0) { bmin = min(bmin, bb[k]); bmax = max(bmax, bb[k]); }
+    }
+    bmin = __reduce_min_sync(kFull, bmin);
+    bmax = __reduce_max_sync(kFull, bmax);
+    if (lane == 0) { atomicMin(&s_bmin, bmin); atomicMax(&s_bmax, bmax); }
+    __syncthreads();
+    bmin = s_bmin; bmax = s_bmax;
   }
-  bmin = __reduce_min_sync(kFull, bmin);
-  bmax = __reduce_max_sync(kFull, bmax);
-  if (lane == 0) { atomicMin(&s_bmin, bmin); atomicMax(&s_bmax, bmax); }
-  __syncthreads();
-  bmin = s_bmin; bmax = s_bmax;
   double* my = p.partial + (size_t)blockIdx.x * p.B * 3;
   for (int b = tid; b < p.B; b += kStatsThreads)
     if (b < bmin || b > bmax) { my[b * 3 + 0] = 0.0; my[b * 3 + 1] = 0.0; my[b * 3 + 2] = 0.0; }
   for (int b = bmin; b <= bmax; ++b) {
     double s = 0.0, s2 = 0.0, c = 0.0;
-    for (int64_t i = i0 + tid; i < i1; i += kStatsThreads) {
-      const float z = p.zbar[i];
-      if (p.bidx[i] == b && z > 0.0f) { s += (double)z; s2 += (double)z * (double)z; c += 1.0; }
+    for (int64_t i = i0 + 4 * tid; i < i1; i += 4 * kStatsThreads) {
+      float zz[4] = {0.f, 0.f, 0.f, 0.f};
+      int bb[4] = {-1, -1, -1, -1};
+      if (i + 4 <= i1) {
+        const float4 tz = *reinterpret_cast<const float4*>(p.zbar + i);
+        const int4 tb = *reinterpret_cast<const int4*>(p.bidx + i);
+        zz[0] = tz.x; zz[1] = tz.y; zz[2] = tz.z; zz[3] = tz.w;
+        bb[0] = tb.x; bb[1] = tb.y; bb[2] = tb.z; bb[3] = tb.w;
+      } else {
+        for (int k = 0; k < 4; ++k) if (i + k < i1) { zz[k] = p.zbar[i + k]; bb[k] = p.bidx[i + k]; }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k)  // element order within a thread is fixed -> deterministic
+        if (bb[k] == b && zz[k] > 0.0f) { s += (double)zz[k]; s2 += (double)zz[k] * (double)zz[k]; c += 1.0; }
     }
     s = warp_sum(s); s2 = warp_sum(s2); c = warp_sum(c);
     if (lane == 0) { red[0][warp] = s; red[1][warp] = s2; red[2][warp] = c; }
@@ -459,6 +480,7 @@ static FwdWs fwd_ws_layout(int64_t N, int B) {
   int64_t chunk = kStatsChunk;
   if (nch > kStatsMaxChunks) {
     chunk = (N + kStatsMaxChunks - 1) / kStatsMaxChunks;
+    chunk = (chunk + 3) / 4 * 4;  // vector loads in the stats kernel
     nch = (N + chunk - 1) / chunk;
   }
   w.nchunks = (int)nch;

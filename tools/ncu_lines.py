@@ -32,7 +32,7 @@ for f in os.listdir(tmp):
                 if m:
                     cur = (os.path.basename(m.group(1)), int(m.group(2)))
                     continue
-                if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+                if re.match(r"\s+/\*[0-9a-f]{4,5}\*/", ln):
                     lst.append(cur)
             if lines is None or abs(len(lst) - len(sass)) < abs(len(lines) - len(sass)):
                 lines = lst
