@@ -144,6 +144,7 @@ def oracle_count_fn(oracle):
 
 def cpu_baseline_bp(levels, steps, warmup):
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1
     for _ in range(max(1, warmup)):
         oracle_step(levels, oracle)
     ts = []
@@ -157,6 +158,7 @@ def cpu_baseline_bp(levels, steps, warmup):
 
 def cpu_baseline_tsdf(n_frames=3):
     import oracle
+    oracle.set_num_threads(os.cpu_count() or 1)
     bnds = np.array([[0.0, 20.48]] * 3)
     v = oracle.TSDFVolumeOracle(bnds, 0.04, margin=3)
     K = synth.tsdf_intrinsics()
@@ -192,7 +194,7 @@ def run_reference(args, rank, world):
         "tsdf": {"frames_per_s": tsdf_fps, "unit": "frames/s", "volume": "512^3 @ 4 cm", "sample": "3 frames, C port"},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
 
 
 # --------------------------------------------------------------------------------------------------
@@ -396,7 +398,7 @@ def run_ours(args, rank, world, local_rank):
     # ---- TSDF leg (rank 0 only; replicas only across ranks) -------------------------------------------
     tsdf = None
     if rank == 0:
-        tsdf = bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf)
+        tsdf = bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, with_cpu=(world == 1))
 
     # ---- aggregate ---------------------------------------------------------------------------------------
     if world > 1:
@@ -441,7 +443,12 @@ def run_ours(args, rank, world, local_rank):
     achieved = alg / (ms_k * 1e-3) / 1e9
     a_path = sum(sum(algorithmic_bytes(l, s)) for l, s in zip(levels, S_levels))
     path_gbs = a_path / (ms_step * 1e-3) / 1e9
-    cpu_v, cpu_sec, cores = cpu_baseline_bp(levels, 5, 1)
+    cpu_base = None
+    if world == 1:  # reported on rank 0 at N=1 only (the ranks of a multi-GPU run share the host cores)
+        cpu_v, cpu_sec, cores = cpu_baseline_bp(levels, 5, 1)
+        cpu_base = {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
+                    "sample": "5 full steps of the same fragment on the host (OpenMP C port of the reference "
+                              "algorithm; %.1f ms/step)" % (cpu_sec * 1e3)}
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -469,15 +476,13 @@ def run_ours(args, rank, world, local_rank):
                           "frac_of_nominal_8TBs": path_gbs / 8000.0},
         "kernel_ms_per_step": {k: v / args.steps for k, v in sorted(tot_ms.items())},
         "kernel_us_per_level": [{k: round(1e3 * v["ms"] / args.steps, 2) for k, v in sorted(acc.items())} for acc in prof],
-        "cpu_baseline": {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "5 full steps of the same fragment on the host (OpenMP C port of the reference "
-                                   "algorithm; %.1f ms/step)" % (cpu_sec * 1e3)},
+        "cpu_baseline": cpu_base,
         "dense_level2": dense,
         "batched_fragments": batched,
         "large_scene": scene,
         "tsdf": tsdf,
     }
-    print(json.dumps(line), flush=True)
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -608,7 +613,12 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     ms = _max_over_ranks(torch, dist, dev, float(np.mean(ts)), world)
-    res = {"index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": int(b1 - b0),
+    from deep3dmap_b200 import _lib
+    torch.cuda.synchronize()
+    _lib.profile_begin()
+    step()
+    kern = {k: round(v["ms"], 3) for k, v in sorted(_lib.profile_end().items())}
+    res = {"kernel_ms_rank0": kern, "index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": int(b1 - b0),
            "samples_per_step": int(N) * V, "valid_samples": int(S[0].item()), "ms_per_step": ms,
            "samples_per_s": N * V / (ms * 1e-3), "scaling": "strong",
            "collectives": "all_reduce(3 fp64 per fragment) + all_reduce(grad_feats %.0f MB) + all_gather(count, %d B/voxel)"
@@ -675,7 +685,7 @@ def bench_dense_l2(torch, dev, _lib, back_project, flush_buf, peak_gbs, steps, p
             "bp_bwd_gather_GBs": (16 * C * S + 4 * V * B * C * H * W + 16 * S) / (gat_ms * 1e-3) / 1e9 if gat_ms else None}
 
 
-def bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=False):
+def bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=False, with_cpu=True):
     """BASELINE configs[2]: 300 synthetic 640x480 depth frames into a 512^3 volume at 4 cm."""
     F = N_TSDF_FRAMES
     K = synth.tsdf_intrinsics()
@@ -742,14 +752,47 @@ def bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=False):
             v.integrate(None, depths[f], K, poses[f], 1.0)
     torch.cuda.synchronize()
     res["e2e_datagen_3level_fps"] = F / (time.perf_counter() - t0)
-    cpu_fps, cores = cpu_baseline_tsdf(3)
-    res["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                           "sample": "3 frames into the same 512^3 volume, OpenMP C port of the reference kernel"}
+    if with_cpu:
+        cpu_fps, cores = cpu_baseline_tsdf(3)
+        res["cpu_baseline"] = {"value": cpu_fps, "unit": "frames/s", "cores": cores, "kind": "port",
+                               "sample": "3 frames into the same 512^3 volume, OpenMP C port of the reference kernel"}
     res["gpu_launches"] = int(vol.gpu_launches)
     return res
 
 
+class _StdoutGuard:
+    """Exactly ONE JSON line may reach stdout: NCCL / torch occasionally print banners on fd 1, so fd 1 is pointed at
+    stderr for the duration of the run and the JSON line is written to the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.write(self.saved, (line + "\n").encode())
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_GUARD = None
+
+
+def emit_json(obj):
+    line = json.dumps(obj)
+    if _GUARD is not None:
+        _GUARD.emit(line)
+    else:
+        print(line, flush=True)
+
+
 def main():
+    global _GUARD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -762,10 +805,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank, world)
-    else:
-        run_ours(args, rank, world, local_rank)
+    with _StdoutGuard() as g:
+        _GUARD = g
+        if args.impl == "reference":
+            run_reference(args, rank, world)
+        else:
+            run_ours(args, rank, world, local_rank)
+        _GUARD = None
 
 
 if __name__ == "__main__":

@@ -14,7 +14,7 @@ SYMBOLS = (
     "d3m_version", "d3m_last_error", "d3m_device_count",
     "d3m_kernel_launches", "d3m_profile_begin", "d3m_profile_end",
     "d3m_feats_nchw_to_nhwc", "d3m_feats_nhwc_to_nchw",
-    "d3m_back_project_fwd_workspace", "d3m_back_project_fwd",
+    "d3m_back_project_fwd_workspace", "d3m_back_project_cell_hist_elems", "d3m_back_project_fwd",
     "d3m_back_project_fwd_partial", "d3m_back_project_fwd_finish",
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
     "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_integrate_host",
@@ -54,6 +54,8 @@ def lib():
         f.restype = i32
     L.d3m_back_project_fwd_workspace.argtypes = [i64, i32, i32, i32]
     L.d3m_back_project_fwd_workspace.restype = sz
+    L.d3m_back_project_cell_hist_elems.argtypes = [i64, i32, i32, i32, i32]
+    L.d3m_back_project_cell_hist_elems.restype = sz
     L.d3m_back_project_fwd.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd.restype = i32
     L.d3m_back_project_fwd_partial.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]

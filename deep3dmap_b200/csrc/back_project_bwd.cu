@@ -48,7 +48,9 @@ struct BwdParams {
   int4* entries;         // {voxel, fx, fy, cell} in slot-claim order (fill)
   int4* sorted;          // the same entries, every cell in ascending voxel order (order)
   float* grad_feats;
-  int64_t M;  // V*B*H*W cells
+  int64_t M;      // V*B*H*W cells
+  int64_t Mb;     // M << nb_log2 bins (cell-major, voxel-bucket-minor; see BinCfg)
+  int nb_log2;
   unsigned long long* scan_state;  // nchunks words, zeroed together with bin_cnt
   unsigned int* counter;           // scan ticket, zeroed together with bin_cnt
   int nchunks;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const Bwd
       load_krcam(p.KR, v, p.B, b, r0, r1, r2);
       const Sample s = project(gx, gy, gz, r0, r1, r2, (float)(p.W - 1), (float)(p.H - 1));
       ok[j] = s.valid;
-      key[j] = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
+      key[j] = ((((v * p.B + b) * p.H + s.y0) * p.W + s.x0) << p.nb_log2) + ((int)n & ((1 << p.nb_log2) - 1));
       fx[j] = s.fx; fy[j] = s.fy;
     }
   }
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdPar
   const int cid = s_cid;
   const int64_t base = (int64_t)cid * kScanChunk + (int64_t)tid * kScanItems;
   int v[kScanItems];
-  if (base + kScanItems <= p.M) {
+  if (base + kScanItems <= p.Mb) {
     const int4* q = reinterpret_cast<const int4*>(p.bin_cnt + base);
 #pragma unroll
     for (int i = 0; i < kScanItems / 4; ++i) {
@@ -199,7 +201,7 @@ __global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdPar
     }
   } else {
 #pragma unroll
-    for (int i = 0; i < kScanItems; ++i) v[i] = (base + i < p.M) ? p.bin_cnt[base + i] : 0;
+    for (int i = 0; i < kScanItems; ++i) v[i] = (base + i < p.Mb) ? p.bin_cnt[base + i] : 0;
   }
   int s = 0;
 #pragma unroll
@@ -237,13 +239,13 @@ __global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdPar
       st[cid] = (2ull << 32) | (unsigned)(prefix + total);
     }
     s_prefix = prefix;
-    if (cid == p.nchunks - 1) p.bin_start[p.M] = prefix + total;
+    if (cid == p.nchunks - 1) p.bin_start[p.Mb] = prefix + total;
   }
   __syncthreads();
   int off = s_prefix + woff + inc - s;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
-    if (base + i < p.M) {
+    if (base + i < p.Mb) {
       p.bin_start[base + i] = off;
       p.bin_cursor[base + i] = off;
     }
@@ -258,7 +260,7 @@ __global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdPar
 // This removes the only nondeterminism of the backward pass (the claim order of the fill atomics).
 constexpr int kOrderThreads = 256;
 __global__ void __launch_bounds__(kOrderThreads) bp_bwd_order_kernel(const BwdParams p) {
-  const int total = __ldg(p.bin_start + p.M);
+  const int total = __ldg(p.bin_start + p.Mb);
   for (int i = blockIdx.x * kOrderThreads + threadIdx.x; i < total; i += gridDim.x * kOrderThreads) {
     const int4 e = __ldg(p.entries + i);
     const int ms = __ldg(p.bin_start + e.w), me = __ldg(p.bin_start + e.w + 1);
@@ -276,22 +278,78 @@ __global__ void __launch_bounds__(kOrderThreads) bp_bwd_order_kernel(const BwdPa
 }
 
 // ---- gather --------------------------------------------------------------------------------------
+// One batch of up to BS entries of a cell, held one per lane (lane j of the group = entry j, .x < 0 = absent): the
+// group issues all BS row loads back to back (BS*R independent 128-bit loads in flight per lane) and then does the
+// arithmetic in entry order.  An absent entry has a zero row: it adds +0 to every sum (no branch needed).
+// Fused multiply-add: one rounding per contribution (aten rounds the product first; the difference is <= 0.5 ulp
+// per term, inside the 1e-5 gradient tolerance) and half the FP instructions of mul + add.
+template <int G, int R, int BS>
+__device__ __forceinline__ void gather_batch(const int4 cur, const int gbase, const int gl, const bool gact,
+                                             const float4* __restrict__ ghat4, float4 (&anw)[R], float4 (&ane)[R],
+                                             float4 (&asw)[R], float4 (&ase)[R]) {
+  constexpr int C4 = G * R;
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 rows[BS][R];
+  float fxs[BS], fys[BS];
+#pragma unroll
+  for (int j = 0; j < BS; ++j) {
+    const int nj = __shfl_sync(kFullB, cur.x, gbase + j);
+    fxs[j] = __int_as_float(__shfl_sync(kFullB, cur.y, gbase + j));
+    fys[j] = __int_as_float(__shfl_sync(kFullB, cur.z, gbase + j));
+    const bool on = gact && nj >= 0;
+    const float4* row = ghat4 + (int64_t)(on ? nj : 0) * C4 + gl;
+#pragma unroll
+    for (int i = 0; i < R; ++i) rows[j][i] = on ? __ldg(row + i * G) : zero4;
+  }
+#pragma unroll
+  for (int j = 0; j < BS; ++j) {
+    const float fx = fxs[j], fy = fys[j];
+    const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy);
+    const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(fx, wy0), sw = __fmul_rn(wx0, fy), se = __fmul_rn(fx, fy);
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const float4 q = rows[j][i];
+      anw[i].x = __fmaf_rn(nw, q.x, anw[i].x); anw[i].y = __fmaf_rn(nw, q.y, anw[i].y);
+      anw[i].z = __fmaf_rn(nw, q.z, anw[i].z); anw[i].w = __fmaf_rn(nw, q.w, anw[i].w);
+      ane[i].x = __fmaf_rn(ne, q.x, ane[i].x); ane[i].y = __fmaf_rn(ne, q.y, ane[i].y);
+      ane[i].z = __fmaf_rn(ne, q.z, ane[i].z); ane[i].w = __fmaf_rn(ne, q.w, ane[i].w);
+      asw[i].x = __fmaf_rn(sw, q.x, asw[i].x); asw[i].y = __fmaf_rn(sw, q.y, asw[i].y);
+      asw[i].z = __fmaf_rn(sw, q.z, asw[i].z); asw[i].w = __fmaf_rn(sw, q.w, asw[i].w);
+      ase[i].x = __fmaf_rn(se, q.x, ase[i].x); ase[i].y = __fmaf_rn(se, q.y, ase[i].y);
+      ase[i].z = __fmaf_rn(se, q.z, ase[i].z); ase[i].w = __fmaf_rn(se, q.w, ase[i].w);
+    }
+  }
+}
+
+__device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
+  return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
+}
+
+constexpr int kBigCell = 256;  // entries from which a cell is processed by the whole CTA instead of one lane group
+constexpr int kMaxBig = 64;    // deferred cells per tile (further ones are simply processed by their own group)
+
 // Shared memory: part[4][ncell][C/4] float4 -- corner-major so that the lane groups of a warp (adjacent cells)
-// touch adjacent addresses in both phases (no bank conflicts, no padding).
+// touch adjacent addresses in both phases (no bank conflicts, no padding) -- then scratch[warps][4][C/4] float4 for
+// the cooperative pass over heavily populated cells.
 template <int G, int R>
-__global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_tile_kernel(const BwdParams p, const int TX,
+__global__ void __launch_bounds__(kGatherWarps * 32, (R == 1 ? 4 : 3)) bp_bwd_gather_tile_kernel(const BwdParams p, const int TX,
                                                                                const int TY, const int tiles_x,
                                                                                const int tiles_y) {
   extern __shared__ __align__(16) unsigned char gsm[];
+  __shared__ int s_big[kMaxBig];
+  __shared__ int s_nbig;
   float4* part = reinterpret_cast<float4*>(gsm);
   constexpr int NG = 32 / G;
   constexpr int C4 = G * R;
   constexpr int kGroups = kGatherWarps * NG;
+  constexpr int BS = (R == 1) ? (G < 8 ? G : 8) : (R == 2 ? 4 : 2);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane / G, gl = lane % G;
   const bool gact = g < NG;
   const int gid = warp * NG + g;
+  const int gbase = g * G;
   const int CW = TX + 1, CH = TY + 1, ncell = CW * CH;
+  float4* scratch = part + 4 * ncell * C4;
   int t = blockIdx.x;
   const int txi = t % tiles_x; t /= tiles_x;
   const int tyi = t % tiles_y;
@@ -300,6 +358,8 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_tile_kernel(c
   const int64_t map_base = (int64_t)map * p.H * p.W;
   const float4* __restrict__ ghat4 = reinterpret_cast<const float4*>(p.ghat);
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) s_nbig = 0;
+  __syncthreads();
 
   // ---- phase 1: cells -> four corner partial sums each ------------------------------------------
   // (row, col) of this group's cell inside the (CH x CW) cell window, advanced by kGroups cells per round
@@ -315,58 +375,31 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_tile_kernel(c
     if (slot) {
       if (cy >= 0 && cx >= 0 && cy < p.H && cx < p.W) {
         const int64_t cell = map_base + (int64_t)cy * p.W + cx;
-        s = __ldg(p.bin_start + cell);
-        e = __ldg(p.bin_start + cell + 1);
+        s = __ldg(p.bin_start + (cell << p.nb_log2));
+        e = __ldg(p.bin_start + ((cell + 1) << p.nb_log2));
+      }
+      if (e - s >= kBigCell) {  // defer to the cooperative pass (list order is irrelevant: cells are independent)
+        int idx = 0;
+        if (gl == 0) idx = atomicAdd(&s_nbig, 1);
+        idx = __shfl_sync(__activemask(), idx, gbase);
+        if (idx < kMaxBig) {
+          if (gl == 0) s_big[idx] = cl;
+          e = s;
+        }
       }
     }
     const int kmax = __reduce_max_sync(kFullB, e - s);
     float4 anw[R], ane[R], asw[R], ase[R];
 #pragma unroll
     for (int i = 0; i < R; ++i) { anw[i] = zero4; ane[i] = zero4; asw[i] = zero4; ase[i] = zero4; }
-    // Entries are taken BS at a time: lane j of the group fetches entry k0+j, the group then issues all BS row loads
-    // back to back (BS*R independent 128-bit loads in flight per lane) before the arithmetic, which runs in entry
-    // order.  The next batch's entries are fetched while the current rows are in flight.
-    constexpr int BS = (R == 1) ? (G < 8 ? G : 8) : (R == 2 ? 4 : 2);
-    const int gbase = g * G;
+    // lane j of the group fetches entry k0+j; the next batch's entries are fetched while the current rows are in flight
     int4 mine = make_int4(-1, 0, 0, 0);
     if (gl < BS && (s + gl) < e) mine = __ldg(p.sorted + s + gl);
     for (int k0 = 0; k0 < kmax; k0 += BS) {
       const int4 cur = mine;
       mine = make_int4(-1, 0, 0, 0);
       if (gl < BS && (s + k0 + BS + gl) < e) mine = __ldg(p.sorted + s + k0 + BS + gl);
-      float4 rows[BS][R];
-      float fxs[BS], fys[BS];
-#pragma unroll
-      for (int j = 0; j < BS; ++j) {
-        const int nj = __shfl_sync(kFullB, cur.x, gbase + j);
-        fxs[j] = __int_as_float(__shfl_sync(kFullB, cur.y, gbase + j));
-        fys[j] = __int_as_float(__shfl_sync(kFullB, cur.z, gbase + j));
-        const bool on = gact && nj >= 0;
-        const float4* row = ghat4 + (int64_t)(on ? nj : 0) * C4 + gl;
-#pragma unroll
-        for (int i = 0; i < R; ++i) rows[j][i] = on ? __ldg(row + i * G) : zero4;
-      }
-#pragma unroll
-      for (int j = 0; j < BS; ++j) {
-        // an absent entry has a zero row: it adds +0 to every sum (no branch needed)
-        const float fx = fxs[j], fy = fys[j];
-        const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy);
-        const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(fx, wy0), sw = __fmul_rn(wx0, fy), se = __fmul_rn(fx, fy);
-#pragma unroll
-        for (int i = 0; i < R; ++i) {
-          const float4 q = rows[j][i];
-          // fused multiply-add: one rounding per contribution (aten rounds the product first; the difference is
-          // <= 0.5 ulp per term, inside the 1e-5 gradient tolerance) and half the FP instructions of mul + add
-          anw[i].x = __fmaf_rn(nw, q.x, anw[i].x); anw[i].y = __fmaf_rn(nw, q.y, anw[i].y);
-          anw[i].z = __fmaf_rn(nw, q.z, anw[i].z); anw[i].w = __fmaf_rn(nw, q.w, anw[i].w);
-          ane[i].x = __fmaf_rn(ne, q.x, ane[i].x); ane[i].y = __fmaf_rn(ne, q.y, ane[i].y);
-          ane[i].z = __fmaf_rn(ne, q.z, ane[i].z); ane[i].w = __fmaf_rn(ne, q.w, ane[i].w);
-          asw[i].x = __fmaf_rn(sw, q.x, asw[i].x); asw[i].y = __fmaf_rn(sw, q.y, asw[i].y);
-          asw[i].z = __fmaf_rn(sw, q.z, asw[i].z); asw[i].w = __fmaf_rn(sw, q.w, asw[i].w);
-          ase[i].x = __fmaf_rn(se, q.x, ase[i].x); ase[i].y = __fmaf_rn(se, q.y, ase[i].y);
-          ase[i].z = __fmaf_rn(se, q.z, ase[i].z); ase[i].w = __fmaf_rn(se, q.w, ase[i].w);
-        }
-      }
+      gather_batch<G, R, BS>(cur, gbase, gl, gact, ghat4, anw, ane, asw, ase);
     }
     if (slot) {
 #pragma unroll
@@ -378,6 +411,55 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_tile_kernel(c
         part[3 * ncell * C4 + o] = ase[i];
       }
     }
+  }
+  __syncthreads();
+  // ---- phase 1b: heavily populated cells, all lane groups of the CTA together -----------------------
+  // Group q takes the batches q, q+kGroups, ... of the cell; the group sums are then added in the fixed order
+  // g = 0..NG-1 inside each warp and w = 0..kGatherWarps-1 across warps (both through the scratch area) -- a pure function of
+  // the cell's entry count, hence deterministic.
+  const int nbig = min(s_nbig, kMaxBig);
+  for (int bi = 0; bi < nbig; ++bi) {
+    const int cl = s_big[bi];
+    const int cy = y0 - 1 + cl / CW, cx = x0 - 1 + cl % CW;
+    const int64_t cell = map_base + (int64_t)cy * p.W + cx;
+    const int s = __ldg(p.bin_start + (cell << p.nb_log2)), e = __ldg(p.bin_start + ((cell + 1) << p.nb_log2));
+    const int nbatch = (e - s + BS - 1) / BS;
+    const int rounds = (nbatch + kGroups - 1) / kGroups;
+    float4 anw[R], ane[R], asw[R], ase[R];
+#pragma unroll
+    for (int i = 0; i < R; ++i) { anw[i] = zero4; ane[i] = zero4; asw[i] = zero4; ase[i] = zero4; }
+    for (int r = 0; r < rounds; ++r) {
+      const int k0 = (r * kGroups + gid) * BS;
+      int4 cur = make_int4(-1, 0, 0, 0);
+      if (gact && gl < BS && (s + k0 + gl) < e) cur = __ldg(p.sorted + s + k0 + gl);
+      gather_batch<G, R, BS>(cur, gbase, gl, gact, ghat4, anw, ane, asw, ase);
+    }
+    // inside the warp: the groups add their sums into the warp's scratch slot one after the other (fixed order)
+#pragma unroll 1
+    for (int gg = 0; gg < NG; ++gg) {
+      if (gact && g == gg) {
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const int o = i * G + gl;
+          float4* q0 = scratch + (warp * 4 + 0) * C4 + o;
+          float4* q1 = scratch + (warp * 4 + 1) * C4 + o;
+          float4* q2 = scratch + (warp * 4 + 2) * C4 + o;
+          float4* q3 = scratch + (warp * 4 + 3) * C4 + o;
+          if (gg == 0) { *q0 = anw[i]; *q1 = ane[i]; *q2 = asw[i]; *q3 = ase[i]; }
+          else { *q0 = add4(*q0, anw[i]); *q1 = add4(*q1, ane[i]); *q2 = add4(*q2, asw[i]); *q3 = add4(*q3, ase[i]); }
+        }
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    for (int o = threadIdx.x; o < 4 * C4; o += kGatherWarps * 32) {  // o = corner * C4 + quad
+      float4 a = scratch[o];
+#pragma unroll
+      for (int w = 1; w < kGatherWarps; ++w) a = add4(a, scratch[w * 4 * C4 + o]);
+      const int corner = o / C4, q = o - corner * C4;
+      part[(corner * ncell + cl) * C4 + q] = a;
+    }
+    __syncthreads();
   }
   __syncthreads();
   // ---- phase 2: texel (y,x) = nw(y,x) + ne(y,x-1) + sw(y-1,x) + se(y-1,x-1), in that order ---------
@@ -428,7 +510,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_generic_kerne
       const int dx = corner & 1, dy = corner >> 1;
       if (x - dx < 0 || y - dy < 0) continue;
       const int64_t cell = t - dx - (int64_t)dy * p.W;
-      const int s = __ldg(p.bin_start + cell), e = __ldg(p.bin_start + cell + 1);
+      const int s = __ldg(p.bin_start + (cell << p.nb_log2)), e = __ldg(p.bin_start + ((cell + 1) << p.nb_log2));
       for (int k = s; k < e; ++k) {
         const int4 en = __ldg(p.sorted + k);
         const float fx = __int_as_float(en.y), fy = __int_as_float(en.z);
@@ -463,13 +545,16 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_generic_kerne
 struct BwdWs {
   size_t ghat, cnt, bin_cnt, bin_cursor, bin_start, scan_state, counter, entries, sorted, total, zero_bytes;
   int nchunks;
-  int64_t M;
+  int64_t M, Mb;
+  BinCfg bc;
 };
 
 static BwdWs bwd_ws_layout(int64_t N, int B, int V, int C, int H, int W) {
   BwdWs w;
   w.M = (int64_t)V * B * H * W;
-  w.nchunks = (int)((w.M + kScanChunk - 1) / kScanChunk);
+  w.bc = bin_config(N, V, w.M);
+  w.Mb = w.M << w.bc.nb_log2;
+  w.nchunks = (int)((w.Mb + kScanChunk - 1) / kScanChunk);
   size_t o = 0;
   const size_t n1 = (size_t)(N > 0 ? N : 1);
   w.ghat = o; o = align_up(o + sizeof(float) * n1 * (size_t)C, 256);
@@ -478,10 +563,10 @@ static BwdWs bwd_ws_layout(int64_t N, int B, int V, int C, int H, int W) {
   // clears the histogram when the forward pass did not hand one over
   w.scan_state = o; o = align_up(o + sizeof(unsigned long long) * (size_t)(w.nchunks + 1), 256);
   w.counter = o; o = align_up(o + 256, 256);
-  w.bin_cnt = o; o = align_up(o + sizeof(int) * (size_t)w.M, 256);
+  w.bin_cnt = o; o = align_up(o + sizeof(int) * (size_t)w.Mb, 256);
   w.zero_bytes = o - w.scan_state;
-  w.bin_cursor = o; o = align_up(o + sizeof(int) * (size_t)w.M, 256);
-  w.bin_start = o; o = align_up(o + sizeof(int) * (size_t)(w.M + 1), 256);
+  w.bin_cursor = o; o = align_up(o + sizeof(int) * (size_t)w.Mb, 256);
+  w.bin_start = o; o = align_up(o + sizeof(int) * (size_t)(w.Mb + 1), 256);
   w.entries = o; o = align_up(o + sizeof(int4) * n1 * (size_t)V, 256);
   w.sorted = o; o = align_up(o + sizeof(int4) * n1 * (size_t)V, 256);
   w.total = o;
@@ -574,6 +659,7 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
     const int tiles_x = (p.W + TX - 1) / TX, tiles_y = (p.H + TY - 1) / TY;
     const int64_t tiles = (int64_t)p.V * p.B * tiles_x * tiles_y;
     D3M_REQUIRE(tiles < (1ll << 31), D3M_ERR_ARG, "back_project backward: too many gather tiles");
+    smem += (size_t)kGatherWarps * 4 * p.C * 4;  // scratch of the cooperative big-cell pass
     D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchScope ls("bp_bwd_gather", stream);
     k<<<(unsigned)tiles, kGatherWarps * 32, smem, stream>>>(p, TX, TY, tiles_x, tiles_y);
@@ -639,7 +725,7 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
   p.entries = reinterpret_cast<int4*>(ws + w.entries);
   p.sorted = reinterpret_cast<int4*>(ws + w.sorted);
   p.grad_feats = grad_feats_nhwc;
-  p.M = w.M;
+  p.M = w.M; p.Mb = w.Mb; p.nb_log2 = w.bc.nb_log2;
   p.nchunks = w.nchunks;
   p.grad_nchw = grad_nchw ? 1 : 0;
   float* cnt_ws = count ? nullptr : reinterpret_cast<float*>(ws + w.cnt);

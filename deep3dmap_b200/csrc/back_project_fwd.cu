@@ -40,7 +40,8 @@ struct FwdParams {
   float* zbar;
   int* bidx;
   unsigned int* counter;  // zeroed here for the stats kernel
-  int* cell_hist;         // optional (V*B*H*W) histogram of valid samples per bilinear cell, consumed by the backward pass
+  int* cell_hist;         // optional histogram of valid samples per (bilinear cell, voxel bucket) bin, consumed by backward
+  int nb_log2;            // BinCfg of this call
   int tv;
   int vchunk;
   int64_t num_tiles;
@@ -63,8 +64,8 @@ __device__ __forceinline__ void bulk_store_tile(float* gdst, const float* ssrc, 
 
 // phase 1 for one chunk of views; returns the number of records pushed by this lane
 template <int KIND>
-__device__ __forceinline__ int push_records(const FwdParams& p, int b, float gx, float gy, float gz, int v0, int v1,
-                                            int lane, int* rec_off, float* rec_fx, float* rec_fy, float& zsum) {
+__device__ __forceinline__ int push_records(const FwdParams& p, int b, int64_t n, float gx, float gy, float gz, int v0,
+                                            int v1, int lane, int* rec_off, float* rec_fx, float* rec_fy, float& zsum) {
   int ccnt = 0;
   if (b >= 0) {
     const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
@@ -74,7 +75,8 @@ __device__ __forceinline__ int push_records(const FwdParams& p, int b, float gx,
       const Sample s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
       if (s.valid) {
         int off = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
-        if (p.cell_hist) atomicAdd(p.cell_hist + off, 1);  // integer RED: order-independent
+        if (p.cell_hist)  // integer RED: order-independent
+          atomicAdd(p.cell_hist + (((int64_t)off << p.nb_log2) + ((int)n & ((1 << p.nb_log2) - 1))), 1);
         if (s.x0 + 1 < p.W) off |= kFlagX1;
         if (s.y0 + 1 < p.H) off |= kFlagY1;
         rec_off[ccnt * 32 + lane] = off;
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
     for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
       const int v1 = min(p.V, v0 + p.vchunk);
       const bool first = (v0 == 0), last = (v1 == p.V);
-      const int ccnt = push_records<KIND>(p, b, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
       cnt += ccnt;
       __syncwarp();
       for (int r = 0; r * NG < p.tv; ++r) {
@@ -250,7 +252,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const Fw
     for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
       const int v1 = min(p.V, v0 + p.vchunk);
       const bool first = (v0 == 0), last = (v1 == p.V);
-      const int ccnt = push_records<KIND>(p, b, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
       cnt += ccnt;
       __syncwarp();
       for (int j = 0; j < p.tv; ++j) {
@@ -572,6 +574,12 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
 
 using namespace d3m;
 
+extern "C" size_t d3m_back_project_cell_hist_elems(int64_t N, int B, int V, int H, int W) {
+  if (N < 0 || B < 1 || V < 1 || H < 1 || W < 1) return 0;
+  const int64_t M = (int64_t)V * B * H * W;
+  return (size_t)(M << bin_config(N, V, M).nb_log2);
+}
+
 extern "C" size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C) {
   (void)V; (void)C;
   if (N < 0 || B < 1) return 0;
@@ -617,7 +625,7 @@ static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float*
   if (rc != D3M_OK) return rc;
   if (cell_hist) {
     D3M_REQUIRE(aligned16(cell_hist), D3M_ERR_ALIGN, "back_project: cell_hist must be 16-byte aligned");
-    D3M_CUDA_CHECK(cudaMemsetAsync(cell_hist, 0, sizeof(int) * (size_t)V * B * H * W, stream));
+    D3M_CUDA_CHECK(cudaMemsetAsync(cell_hist, 0, sizeof(int) * d3m_back_project_cell_hist_elems(N, B, V, H, W), stream));
   }
   if (N == 0) {
     if (depth_sums) D3M_CUDA_CHECK(cudaMemsetAsync(depth_sums, 0, sizeof(double) * 3 * (size_t)B, stream));
@@ -629,6 +637,10 @@ static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float*
   p.coords = coords; p.N = N; p.origin = origin; p.B = B; p.vs = voxel_size;
   p.feats = feats_nhwc; p.V = V; p.C = C; p.H = H; p.W = W; p.KR = KRcam;
   p.out = out; p.count = count; p.cell_hist = cell_hist;
+  {
+    const BinCfg bc = bin_config(N, V, (int64_t)V * B * H * W);
+    p.nb_log2 = bc.nb_log2;
+  }
   p.zbar = reinterpret_cast<float*>(ws + w.zbar);
   p.bidx = reinterpret_cast<int*>(ws + w.bidx);
   p.counter = reinterpret_cast<unsigned int*>(ws + w.counter);

@@ -36,6 +36,27 @@ struct LaunchScope {
 };
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ------------------------------------------------------------------------------------------------
+// Backward binning.  A bin = (bilinear cell (v,b,y0,x0), voxel bucket n & (nb-1)): bins are ordered cell-major,
+// bucket-minor, so a cell's entries stay contiguous; inside a bin the entries are ranked by voxel index.  The resulting
+// accumulation order per cell -- (low bits of the voxel index, voxel index) -- is a pure function of the inputs, which
+// is all determinism needs.  More buckets (nb = 2^nb_log2) shorten the bins of heavily populated cells (a distant wall
+// of a large scene lands thousands of voxels in one cell and ranking is quadratic in the bin length); the LOW bits
+// are used because the voxels that share a cell are spatially clustered, i.e. share their high index bits.  The price
+// is nb x larger scan arrays, so nb grows with the number of potential samples per cell.
+// Pure function of the call's shapes: forward (histogram) and backward (scan / fill / order / gather) agree on it.
+// ------------------------------------------------------------------------------------------------
+struct BinCfg {
+  int nb_log2;  // buckets per cell = 1 << nb_log2; bucket = voxel index & ((1 << nb_log2) - 1)
+};
+static inline BinCfg bin_config(int64_t N, int V, int64_t M) {
+  BinCfg c;
+  c.nb_log2 = 0;
+  const double per_cell = M > 0 ? (double)N * V / (double)M : 0.0;
+  while (c.nb_log2 < 6 && per_cell > 32.0 * (double)(1 << c.nb_log2) && (M << (c.nb_log2 + 1)) < (1ll << 30)) ++c.nb_log2;
+  return c;
+}
 __host__ __device__ static inline int align_up_dev(int x) { return (x + 15) & ~15; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

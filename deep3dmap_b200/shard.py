@@ -110,7 +110,7 @@ class _CudaLocalOps:
         sums = torch.zeros((B, 3), dtype=torch.float64, device=dev)
         hist = None
         if want_hist:
-            hist = (torch.empty if N > 0 else torch.zeros)((V, B, H, W), dtype=torch.int32, device=dev)
+            hist = voxel._new_cell_hist(N, B, V, H, W, dev)
         ws, ws_bytes = voxel._workspace("f", (max(N, 1), B, V, C), dev)
         if N > 0:
             with voxel._on_device(dev):

@@ -44,6 +44,14 @@ class _on_device:
 _ws_cache = {}
 
 
+def _new_cell_hist(N, B, V, H, W, dev):
+    key = ("h", N, B, V, H, W)
+    n = _ws_cache.get(key)
+    if n is None:
+        n = _ws_cache[key] = _lib.lib().d3m_back_project_cell_hist_elems(N, B, V, H, W)
+    return (torch.empty if N > 0 else torch.zeros)((n,), dtype=torch.int32, device=dev)
+
+
 def _workspace(kind, key, dev):
     """Workspace byte count is a pure function of the shapes: cache the ctypes query; the buffer itself comes
     from torch's caching allocator (stream-ordered reuse, graph-capture safe)."""
@@ -102,7 +110,7 @@ def _prep_small(coords, origin, KRcam, device):
 
 def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam, cell_hist=False):
     """Kernel-level forward on channels-last maps (V,B,H,W,C).  Returns (volume (N,C+1), count (N,)) and, with
-    cell_hist=True, additionally the (V,B,H,W) int32 per-cell sample histogram the backward pass starts from."""
+    cell_hist=True, additionally the int32 per-bin sample histogram the backward pass starts from."""
     L = _lib.lib()
     dev = feats_nhwc.device
     V, B, H, W, C = feats_nhwc.shape
@@ -113,7 +121,7 @@ def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam, cell_his
     count = torch.empty((N,), dtype=torch.float32, device=dev)
     hist = None
     if cell_hist:
-        hist = (torch.empty if N > 0 else torch.zeros)((V, B, H, W), dtype=torch.int32, device=dev)
+        hist = _new_cell_hist(N, B, V, H, W, dev)
     if N > 0:
         ws, ws_bytes = _workspace("f", (N, B, V, C), dev)
         with _on_device(dev):

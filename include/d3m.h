@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 101
+#define D3M_VERSION 102
 
 enum {
   D3M_OK = 0,
@@ -74,13 +74,15 @@ int d3m_feats_nhwc_to_nchw(const float* src, float* dst, int64_t n_maps, int C, 
  *   out         (N,C+1) float32: view-mean features | normalised mean depth   (written for every row;
  *               rows whose batch index is outside [0,B) are zero, as in the reference)
  *   count       (N,) float32: number of views that see the voxel (bit-exact contract)
- *   cell_hist   NULL, or (V,B,H,W) int32 (16-byte aligned): receives the number of valid samples per bilinear cell
- *               (v,b,y0,x0).  It is the first step of the deterministic backward; producing it here, where every
- *               voxel is projected anyway, saves the backward one full projection pass.  Pass it to
- *               d3m_back_project_bwd for the SAME coords / KRcam (the autograd wrapper does when feats needs grad).
+ *   cell_hist   NULL, or d3m_back_project_cell_hist_elems(N,B,V,H,W) int32 (16-byte aligned): receives the number of
+ *               valid samples per bin = (bilinear cell (v,b,y0,x0), voxel-index bucket).  It is the first step of the
+ *               deterministic backward; producing it here, where every voxel is projected anyway, saves the backward
+ *               one full projection pass.  Pass it to d3m_back_project_bwd for the SAME coords / KRcam (the autograd
+ *               wrapper does when feats needs grad).
  * workspace: d3m_back_project_fwd_workspace(N,B,V,C) bytes, 256-byte aligned.
  * ------------------------------------------------------------------------------------------- */
 size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C);
+size_t d3m_back_project_cell_hist_elems(int64_t N, int B, int V, int H, int W);
 int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                          float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
                          const float* KRcam, float* out, float* count, int* cell_hist, void* workspace,
@@ -110,7 +112,7 @@ int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sum
  *   grad_out         (N,C+1) float32 (the depth column carries no gradient to feats)
  *   count            (N,) float32 as returned by d3m_back_project_fwd for the same inputs, or NULL
  *                    (then the view counts are recomputed by one extra kernel)
- *   cell_hist        (V,B,H,W) int32 as produced by d3m_back_project_fwd for the same inputs (read-only here, so
+ *   cell_hist        histogram produced by d3m_back_project_fwd for the same inputs (read-only here, so
  *                    backward may run more than once), or NULL (then one extra projection pass rebuilds it)
  *   grad_feats       float32, fully overwritten; (V,B,H,W,C) when grad_nchw == 0, the reference's
  *                    (V,B,C,H,W) when grad_nchw != 0 (the gather kernel then stores channel-strided)
