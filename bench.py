@@ -39,6 +39,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+def ncu_traffic(kernel, level):
+    """DRAM bytes (read + write) of one launch of `kernel` at `level`, from the committed `ncu --set full` capture of
+    `bench.py --profile-step bp` (profiles/roofline_traffic.json, written by tools/summarise_profiles.py)."""
+    p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    try:
+        t = json.load(open(p))
+        return t["kernels"][kernel][level], t["source"]
+    except Exception:
+        return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -259,8 +270,11 @@ def run_ours(args, rank, world, local_rank):
         # target for `ncu`: nothing but K flushed steps of the hot path (no JSON; numbers under a profiler are not bench values)
         for _ in range(args.steps):
             flush_buf.fill_(1)
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()  # with `ncu --profile-from-start off` only these launches are captured
             step_resident()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
         return
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -441,6 +455,7 @@ def run_ours(args, rank, world, local_rank):
     else:
         alg = a_bwd
     achieved = alg / (ms_k * 1e-3) / 1e9
+    traffic, traffic_src = ncu_traffic(dom, li)
     a_path = sum(sum(algorithmic_bytes(l, s)) for l, s in zip(levels, S_levels))
     path_gbs = a_path / (ms_step * 1e-3) / 1e9
     cpu_base = None
@@ -467,7 +482,8 @@ def run_ours(args, rank, world, local_rank):
         "step_mode": "cuda_graph_replay" if ms_graph is not None else "eager", "ms_per_step_eager": ms_eager,
         "ms_per_step_graph": ms_graph, "graph_error": graph_err,
         "roofline": {"bound": "hbm", "kernel": dom, "level": li, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": int(alg), "ms_per_launch": ms_k,
                      "kernel_share_of_step": tot_ms[dom] / kern_total,
                      "note": "feature maps are L2-resident at fragment size (SURVEY §8d): bytes are algorithmic "

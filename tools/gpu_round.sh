@@ -10,12 +10,14 @@ echo "== smoke" ; timeout 300 python -c 'import __graft_entry__ as g; g.smoke()'
 echo "== bench" ; timeout 900 python bench.py --steps 20 --warmup 3 > $OUT/bench.json 2> $OUT/bench.err ; echo "bench rc=$?" ; tail -3 $OUT/bench.err ; cat $OUT/bench.json
 echo "== bench reference" ; timeout 600 python bench.py --impl reference --steps 5 --warmup 1 > $OUT/bench_ref.json 2> $OUT/bench_ref.err ; echo "ref rc=$?" ; cat $OUT/bench_ref.json
 echo "== ncu launch list (bp step)"
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches_bp.csv python bench.py --profile-step bp --steps 2 --warmup 3 --no-graph > $OUT/ncu_bp.log 2>&1 ; echo "rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches_bp.csv python bench.py --profile-step bp --steps 2 --warmup 3 --no-graph > $OUT/ncu_bp.log 2>&1 ; echo "rc=$?"
 echo "== ncu launch list (dense + tsdf)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches_dense.csv python bench.py --profile-step dense --steps 1 --warmup 3 --no-graph > $OUT/ncu_dense.log 2>&1 ; echo "rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv --log-file $OUT/launches_tsdf.csv python bench.py --profile-step tsdf --steps 1 --warmup 3 --no-graph > $OUT/ncu_tsdf.log 2>&1 ; echo "rc=$?"
 echo "== ncu full: dense level-2 fwd + bwd kernels"
 timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o $OUT/prof_dense -f python bench.py --profile-step dense --steps 1 --warmup 3 --no-graph > $OUT/ncu_full_dense.log 2>&1 ; echo "rc=$?"
+echo "== ncu full: headline fragment step (roofline.traffic)"
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -o $OUT/prof_bp -f python bench.py --profile-step bp --steps 1 --warmup 3 --no-graph > $OUT/ncu_full_bp.log 2>&1 ; echo "rc=$?"
 echo "== ncu full: tsdf"
 timeout 600 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:tsdf_integrate -c 2 -o $OUT/prof_tsdf -f python bench.py --profile-step tsdf --steps 1 --warmup 3 --no-graph > $OUT/ncu_full_tsdf.log 2>&1 ; echo "rc=$?"
 ls -la $OUT

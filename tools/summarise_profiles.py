@@ -64,6 +64,35 @@ def full(rep, out):
             w.writerow([r[c].split("(")[0].replace("void ", "") if c == cols[0] else r[c] for c in cols])
 
 
+LIB_NAMES = {"bp_fwd_kernel": "bp_fwd", "bp_stats_kernel": "bp_fwd_stats", "bp_normalise_kernel": "bp_fwd_normalise",
+             "bp_scan_ghat_kernel": "bp_bwd_scan_ghat", "bp_bwd_order_kernel": "bp_bwd_order",
+             "bp_bwd_gather_tile_kernel": "bp_bwd_gather", "transpose_maps_kernel": "relayout_transpose"}
+
+
+def traffic(rep, out, tag):
+    """profiles/roofline_traffic.json: per library kernel name, DRAM read+write bytes of its launch at level 0, 1, 2 of
+    the headline fragment step (launch order inside one captured step = level order)."""
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    if len(rows) < 3:
+        return
+    hdr, units = rows[0], rows[1]
+    kn, rd, wr = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = {}
+    for r in rows[2:]:
+        name = r[kn].split("(")[0].replace("void ", "").replace("d3m::", "").split("<")[0]
+        if name == "bp_bwd_sample_kernel":
+            name = "bp_bwd_fill" if ", 1>" in r[kn].replace("(bool)", "").replace("(int)", "") or "true" in r[kn] else "bp_bwd_hist"
+        else:
+            name = LIB_NAMES.get(name, name)
+        b = float(r[rd]) * scale.get(units[rd], 1.0) + float(r[wr]) * scale.get(units[wr], 1.0)
+        per.setdefault(name, []).append(int(b))
+    json.dump({"source": "profiles/%s_ncu_bp.csv (ncu --set full of `bench.py --profile-step bp`, one flushed step)" % tag,
+               "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)", "kernels": per},
+              open(out, "w"), indent=1)
+
+
 def main():
     tag = sys.argv[1]
     src = os.path.join(ROOT, "gpurun_out", tag)
@@ -75,10 +104,12 @@ def main():
             launches(p, os.path.join(dst, "%s_%s" % (tag, fn)))
         elif fn.endswith(".ncu-rep"):
             full(p, os.path.join(dst, "%s_ncu_%s.csv" % (tag, fn[:-8].replace("prof_", ""))))
+            if fn == "prof_bp.ncu-rep":
+                traffic(p, os.path.join(dst, "roofline_traffic.json"), tag)
         elif fn.startswith("bench") and fn.endswith(".json") and os.path.getsize(p):
             lines = [json.loads(l) for l in open(p) if l.strip().startswith("{")]
             json.dump(lines if len(lines) != 1 else lines[0], open(os.path.join(dst, "%s_%s" % (tag, fn)), "w"), indent=1)
-        elif fn in ("gpu.txt", "pytest_gpu.log", "smoke.log"):
+        elif fn in ("gpu.txt", "pytest_gpu.log", "smoke.log", "tsdf_host_profile.txt"):
             open(os.path.join(dst, "%s_%s" % (tag, fn)), "w").write(open(p).read())
     print(sorted(os.listdir(dst)))
 
