@@ -585,7 +585,7 @@ def bench_batched_fragments(torch, dist, dev, back_project, levels, flush_buf, r
 
 def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     """BASELINE configs[4]: 1024^3 index space @ 4 cm, 64 views, finest level (C=24, 120x160 maps), wall-shell sparse set
-    (~1 % occupancy), voxel-range sharded: feats / KRcam replicated, each rank gathers its contiguous slice; per step
+    (~1 % occupancy), voxel-range sharded (block-cyclic ranges): feats / KRcam replicated, each rank gathers its slice; per step
     one all-reduce of 3 fp64 scalars (depth normalisation), one all-reduce of grad_feats (118 MB) and one all-gather of
     the per-shard view counts (the occupancy slab the next coarse-to-fine level needs)."""
     from deep3dmap_b200 import shard
@@ -593,8 +593,11 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     L = synth.LEVELS[lv]
     coords_all = synth.large_scene_coords(dtype=np.int32)
     N = coords_all.shape[0]
-    b0, b1 = shard.voxel_range(N, rank, world)
-    coords = torch.from_numpy(np.ascontiguousarray(coords_all[b0:b1])).to(dev)
+    # block-cyclic ranges: the camera lattice covers the scene unevenly, contiguous ranges would be unbalanced
+    mine = shard.voxel_blocks(N, rank, world)
+    coords = torch.from_numpy(np.ascontiguousarray(coords_all[mine.numpy()])).to(dev)
+    n_local = int(mine.numel())
+    inv_perm = shard.blocks_inverse_permutation(N, world).to(dev) if world > 1 else None
     del coords_all
     R, c = synth.large_scene_cameras(V)
     KR = torch.from_numpy(synth.krcam_from(R, c, synth.scaled_K(L["scale"]))[:, None].copy()).to(dev)
@@ -603,14 +606,15 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     gen.manual_seed(777)  # same seed on every rank: replicated feature maps
     feats = torch.randn((V, 1, L["C"], L["H"], L["W"]), device=dev, generator=gen).requires_grad_(True)
     gen.manual_seed(778 + rank)
-    go = torch.randn((b1 - b0, L["C"] + 1), device=dev, generator=gen)
-    sizes = [shard.voxel_range(N, r, world)[1] - shard.voxel_range(N, r, world)[0] for r in range(world)]
+    go = torch.randn((n_local, L["C"] + 1), device=dev, generator=gen)
+    sizes = [int(shard.voxel_blocks(N, r, world).numel()) for r in range(world)]
 
     def step():
         feats.grad = None
         vol, cnt = shard.back_project_voxel_sharded(coords, origin, synth.VOXEL_SIZE, feats, KR)
         vol.backward(go)
-        return shard.all_gather_rows(cnt, sizes=sizes), cnt
+        full = shard.all_gather_rows(cnt, sizes=sizes)
+        return (full[inv_perm] if inv_perm is not None else full), cnt  # occupancy in the scene's voxel order
 
     for _ in range(2):
         full_cnt, cnt = step()
@@ -634,7 +638,7 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     _lib.profile_begin()
     step()
     kern = {k: round(v["ms"], 3) for k, v in sorted(_lib.profile_end().items())}
-    res = {"kernel_ms_rank0": kern, "index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": int(b1 - b0),
+    res = {"kernel_ms_rank0": kern, "index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": n_local, "partition": "block-cyclic voxel ranges (4096 voxels per block)",
            "samples_per_step": int(N) * V, "valid_samples": int(S[0].item()), "ms_per_step": ms,
            "samples_per_s": N * V / (ms * 1e-3), "scaling": "strong",
            "collectives": "all_reduce(3 fp64 per fragment) + all_reduce(grad_feats %.0f MB) + all_gather(count, %d B/voxel)"

@@ -5,7 +5,8 @@ the box, gloo in the CPU tests) for the few exchange steps the path really has (
     the fragments, DDP runs `samples_per_gpu=1`): `fragments_of_rank` deals fragments round-robin; there is NO
     data-path collective, forward or backward.
   * voxel-range sharding (BASELINE config 5) -- `voxel_range` splits the (sorted) coordinate list into
-    `world_size` contiguous slices; feats and KRcam are replicated.  `back_project_voxel_sharded` then needs
+    `world_size` contiguous slices (`voxel_blocks`: many block-cyclic ranges per rank, for load balance when the
+    views cover the scene unevenly); feats and KRcam are replicated.  `back_project_voxel_sharded` then needs
       (1) one all-reduce of 3 fp64 scalars per fragment for the depth normalisation (`back_project.py:77-80`),
       (2) in backward, one all-reduce(sum) of grad_feats (every rank holds the partial sums of its voxels), and
       (3) `all_gather_rows` of the per-shard count / occupancy (or full rows) only where the next coarse-to-fine
@@ -47,6 +48,28 @@ def voxel_range(n_voxels, rank=None, world_size=None, group=None):
     q, r = divmod(int(n_voxels), int(world_size))
     begin = rank * q + min(rank, r)
     return begin, begin + q + (1 if rank < r else 0)
+
+
+def voxel_blocks(n_voxels, rank=None, world_size=None, group=None, block=4096):
+    """Block-cyclic variant of `voxel_range` for scenes whose work per voxel is uneven (a camera lattice sees some
+    regions of a large scene far more often than others): the list is cut into `block`-voxel ranges and rank r owns
+    ranges r, r+W, r+2W, ...  Returns the int64 index vector of this rank's voxels (ascending).  The concatenation of
+    the ranks' slices is a permutation of the list; `blocks_inverse_permutation` restores the original order after an
+    `all_gather_rows`."""
+    if rank is None or world_size is None:
+        rank, world_size = _world(group)
+    n_blocks = (int(n_voxels) + block - 1) // block
+    mine = torch.arange(rank, max(n_blocks, rank), world_size, dtype=torch.int64)  # empty when rank >= n_blocks
+    idx = (mine[:, None] * block + torch.arange(block, dtype=torch.int64)[None, :]).reshape(-1)
+    return idx[idx < n_voxels]
+
+
+def blocks_inverse_permutation(n_voxels, world_size, block=4096):
+    """perm such that cat_r(x[voxel_blocks(N, r, W)])[perm] == x."""
+    cat = torch.cat([voxel_blocks(n_voxels, r, world_size, block=block) for r in range(world_size)])
+    inv = torch.empty_like(cat)
+    inv[cat] = torch.arange(cat.numel(), dtype=torch.int64)
+    return inv
 
 
 def tsdf_slab(dim_x, rank=None, world_size=None, group=None, align=8):

@@ -128,3 +128,11 @@ def test_partitions_cover_everything():
         sl = [shard.tsdf_slab(512, k, w) for k in range(w)]
         assert sl[0][0] == 0 and sl[-1][1] == 512 and all(b % 8 == 0 for b, _ in sl)
     assert sorted(sum((shard.fragments_of_rank(64, k, 8) for k in range(8)), [])) == list(range(64))
+    import torch
+    for n, w, blk in ((10, 3, 4), (100003, 8, 4096), (4096, 2, 4096), (5, 8, 2)):
+        parts = [shard.voxel_blocks(n, k, w, block=blk) for k in range(w)]
+        cat = torch.cat(parts)
+        assert sorted(cat.tolist()) == list(range(n))
+        x = torch.arange(n) * 3 + 1
+        inv = shard.blocks_inverse_permutation(n, w, block=blk)
+        assert torch.equal(torch.cat([x[p] for p in parts])[inv], x)
