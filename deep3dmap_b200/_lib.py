@@ -19,6 +19,13 @@ SYMBOLS = (
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
     "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_integrate_host",
     "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches",
+    # level glue around back_project
+    "d3m_grid_coords", "d3m_upsample", "d3m_aligned_camera_coords", "d3m_gather_targets", "d3m_occupancy_flags",
+    "d3m_compact_workspace", "d3m_compact", "d3m_drop_ranks", "d3m_gather_rows", "d3m_gather_concat",
+    "d3m_batch_counts",
+    # sparse <-> dense movement of the fusion volumes
+    "d3m_sparse_to_dense_workspace", "d3m_sparse_to_dense", "d3m_fbv_mask", "d3m_dense_union_flags",
+    "d3m_unravel_coords", "d3m_dense_gather", "d3m_coords_add",
 )
 
 COORDS_F32, COORDS_I64, COORDS_I32 = 0, 1, 2
@@ -84,6 +91,32 @@ def lib():
     L.d3m_tsdf_download.restype = i32
     L.d3m_tsdf_last_launches.argtypes = [vp]
     L.d3m_tsdf_last_launches.restype = i32
+    sigs = {
+        "d3m_grid_coords": [i32, i32, i32, i32, i32, vp, vp, vp],
+        "d3m_upsample": [vp, i32, vp, i64, i32, i32, i32, vp, vp, vp],
+        "d3m_aligned_camera_coords": [vp, i32, i64, vp, i32, f32, vp, vp, vp],
+        "d3m_gather_targets": [vp, i32, i64, i32, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp],
+        "d3m_occupancy_flags": [vp, i64, vp, f32, vp, f32, i64, vp, vp],
+        "d3m_compact": [vp, i64, i32, vp, vp, vp, vp, sz, vp],
+        "d3m_drop_ranks": [vp, i64, i64, vp, vp, vp],
+        "d3m_gather_rows": [vp, i64, vp, i64, vp, vp],
+        "d3m_gather_concat": [ctypes.POINTER(vp), ctypes.POINTER(i32), i32, vp, i64, vp, vp],
+        "d3m_batch_counts": [vp, i32, i64, i32, vp, vp],
+        "d3m_sparse_to_dense": [vp, i64, vp, f32, i32, f32, i32, i32, i32, vp, vp, vp, sz, vp],
+        "d3m_fbv_mask": [vp, i64, ctypes.POINTER(i64), i32, i32, i32, vp, vp, vp, vp],
+        "d3m_dense_union_flags": [vp, vp, i64, i32, i32, vp, vp],
+        "d3m_unravel_coords": [vp, i64, i32, i32, ctypes.POINTER(i64), i64, i32, i64, vp, vp],
+        "d3m_dense_gather": [vp, i32, i32, i32, i32, vp, i64, vp, vp, vp],
+        "d3m_coords_add": [vp, i64, ctypes.POINTER(i64), vp, vp],
+    }
+    for name, args in sigs.items():
+        f = getattr(L, name)
+        f.argtypes = args
+        f.restype = i32
+    L.d3m_compact_workspace.argtypes = [i64]
+    L.d3m_compact_workspace.restype = sz
+    L.d3m_sparse_to_dense_workspace.argtypes = [i32, i32, i32]
+    L.d3m_sparse_to_dense_workspace.restype = sz
     _lib = L
     return L
 

@@ -6,6 +6,11 @@
  *   back_project(coords, origin, voxel_size, feats, KRcam)      deep3dmap/core/voxel/back_project.py:5-84
  *   TSDFVolume.__init__/integrate/get_volume                    deep3dmap/core/tsdf/tsdf_volume.py:14-307
  *   TSDFVolumeTorch.integrate (dataloader variant)              deep3dmap/core/tsdf/tsdf_volume.py:437-574
+ * and the callers either side of that path:
+ *   generate_grid / NeuConNet.upsample / get_target / level glue   deep3dmap/core/voxel/generate_grids.py:4-11,
+ *                                                                deep3dmap/models/neucon_network.py:52-89, 113-207
+ *   GRUFusion sparse<->dense movement, sparse_to_dense_*           deep3dmap/models/modulars/gru_fusion.py:51-181,
+ *                                                                deep3dmap/core/utils/neucon_utils.py:114-131
  *
  * Conventions
  *   - plain pointers and sizes only; no torch / CUDA-runtime types in the signatures.  `stream` is a
@@ -28,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 102
+#define D3M_VERSION 103
 
 enum {
   D3M_OK = 0,
@@ -172,6 +177,95 @@ int d3m_tsdf_download(d3m_tsdf* h, float* tsdf_host, float* weight_host, float* 
 /* voxels whose weight changed in the last integrate call is not tracked; this returns the number of
  * tile launches of the last call (diagnostics for bench.py's gpu_launches) */
 int d3m_tsdf_last_launches(d3m_tsdf* h);
+
+/* =============================================================================================
+ * the steps either side of back_project in the coarse-to-fine level loop
+ * (deep3dmap/models/neucon_network.py:113-207).  Integer / index work is bit-exact.
+ * ========================================================================================== */
+
+/* generate_grid (core/voxel/generate_grids.py:4-11) and the [b | x y z] rows built from it for every fragment
+ * (models/neucon_network.py:118-122).  Per axis the grid holds arange(0, n, interval), x slowest, z fastest.
+ *   coords  NULL or (B*n, 4) float32 rows [b, x, y, z], fragment-major;  grid3  NULL or (3, n) float32 planes. */
+int d3m_grid_coords(int nx, int ny, int nz, int interval, int B, float* coords, float* grid3, void* stream);
+
+/* NeuConNet.upsample (models/neucon_network.py:68-89): every voxel becomes `num` (1..8) children, child i adding
+ * `interval` to the axes of pos_list[i-1]; features are repeated.  Either half may be skipped with NULL.
+ *   pre_coords (N,4) of coords_kind -> up_coords (N*num,4) same dtype;  pre_feat (N,C) -> up_feat (N*num,C). */
+int d3m_upsample(const void* pre_coords, int coords_kind, const float* pre_feat, int64_t N, int C, int interval,
+                 int num, void* up_coords, float* up_feat, void* stream);
+
+/* models/neucon_network.py:143-154: r = [xyz*voxel_size + origin[b], 1] @ world_to_aligned_camera[b,:3,:]^T written
+ * as rows [rx, ry, rz, b] float32 (batch index moved to the last column).  world_to_aligned_camera is (B,4,4). */
+int d3m_aligned_camera_coords(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                              float voxel_size, const float* world_to_aligned_camera, float* r_coords, void* stream);
+
+/* NeuConNet.get_target (models/neucon_network.py:52-65): tsdf_out[n] = tsdf_vol[b, x//d, y//d, z//d] and the same for
+ * the boolean occupancy volume, volumes (B,X,Y,Z).  Negative indices wrap once like torch; rows that are still out of
+ * range (torch raises IndexError) are counted in *bad_rows (device int) and left unwritten. */
+int d3m_gather_targets(const void* coords, int coords_kind, int64_t N, int divisor, const float* tsdf_vol,
+                       const uint8_t* occ_vol, int B, int X, int Y, int Z, float* tsdf_out, uint8_t* occ_out,
+                       int* bad_rows, void* stream);
+
+/* models/neucon_network.py:181-182: flags[n] = occ[n*occ_stride] > threshold  and  grid_mask[n], the mask being an
+ * explicit bool array and / or `count[n] > min_count` (":132 grid_mask = count > 1"); NULL = not applied. */
+int d3m_occupancy_flags(const float* occ, int64_t occ_stride, const float* count, float min_count,
+                        const uint8_t* grid_mask, float threshold, int64_t N, uint8_t* flags, void* stream);
+
+/* Ordered stream compaction == torch.nonzero(flags) / boolean-mask indexing: out[k] = position (or values[position])
+ * of the k-th set (invert != 0: cleared) flag, *total_dev = their number.  `out` must hold N entries.  Deterministic. */
+size_t d3m_compact_workspace(int64_t N);
+int d3m_compact(const uint8_t* flags, int64_t N, int invert, const int64_t* values, int64_t* out, int64_t* total_dev,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* models/neucon_network.py:190-194 (training-time subsampling): keep[r] = 1 for r < n_keep, then keep[choice[j]] = 0;
+ * compacting the index list with `keep` equals `occupancy[ind[choice]] = False`.  *bad counts out-of-range choices. */
+int d3m_drop_ranks(const int64_t* choice, int64_t n_choice, int64_t n_keep, uint8_t* keep, int* bad, void* stream);
+
+/* dst[m] = src[ind[m]] for rows of row_bytes (multiple of 4) bytes; and the fused
+ * cat([a[ind], b[ind], ...], dim=1) of models/neucon_network.py:203-207 for up to 4 float32 sources
+ * (ind == NULL: identity, i.e. a plain row-wise concatenation). */
+int d3m_gather_rows(const void* src, int64_t row_bytes, const int64_t* ind, int64_t M, void* dst, void* stream);
+int d3m_gather_concat(const float* const* srcs_host, const int* widths_host, int n_src, const int64_t* ind, int64_t M,
+                      float* dst, void* stream);
+
+/* rows per fragment (models/neucon_network.py:197-201 aborts the level when a fragment has none) */
+int d3m_batch_counts(const void* coords, int coords_kind, int64_t N, int B, int64_t* counts, void* stream);
+
+/* =============================================================================================
+ * sparse <-> dense movement of the GRU-fusion global volume
+ * (deep3dmap/models/modulars/gru_fusion.py:51-181, deep3dmap/core/utils/neucon_utils.py:114-131).
+ * Coordinates are int64 (M,3) rows, volumes are (X,Y,Z,c) float32 C-order.
+ * ========================================================================================== */
+
+/* sparse_to_dense_torch / sparse_to_dense_channel: dense = full(default); dense[locs] = values ((M,c) rows, or
+ * scalar_value when values == NULL).  With a workspace (d3m_sparse_to_dense_workspace bytes) duplicate locations are
+ * resolved deterministically -- the last row wins, as on the reference's CPU path; without one the caller guarantees
+ * unique locations.  Out-of-range rows are counted in *bad_rows and skipped. */
+size_t d3m_sparse_to_dense_workspace(int X, int Y, int Z);
+int d3m_sparse_to_dense(const int64_t* locs, int64_t M, const float* values, float scalar_value, int c,
+                        float default_val, int X, int Y, int Z, float* dense, int* bad_rows, void* workspace,
+                        size_t workspace_bytes, void* stream);
+
+/* gru_fusion.py:83-91: shifted = global_coords - relative_origin; valid = inside the fragment bounding volume and,
+ * when occupied_volume (X,Y,Z) is given (FUSION.FULL == False), occupied_volume[shifted] != 0. */
+int d3m_fbv_mask(const int64_t* global_coords, int64_t M, const int64_t* relative_origin3_host, int X, int Y, int Z,
+                 const float* occupied_volume, int64_t* shifted, uint8_t* valid, void* stream);
+
+/* gru_fusion.py:100-106: flags[i] = any_c(pred(a[i,c])) | any_c(pred(b[i,c])), pred = (v != 0) for mode 0 and
+ * (|v| < 1) for mode 1; vol_b may be NULL.  Compact the flags to get torch.nonzero's row-major order. */
+int d3m_dense_union_flags(const float* vol_a, const float* vol_b, int64_t n_vox, int c, int mode, uint8_t* flags,
+                          void* stream);
+
+/* linear index -> rows ((x,y,z) + add3) * multiplier, optionally prefixed by batch_index (gru_fusion.py:145, 288) */
+int d3m_unravel_coords(const int64_t* linear, int64_t M, int Y, int Z, const int64_t* add3_host, int64_t multiplier,
+                       int with_batch, int64_t batch_index, int64_t* out, void* stream);
+
+/* out[k,:] = volume[coords[k]] (gru_fusion.py:256-261); out-of-range rows counted in *bad_rows */
+int d3m_dense_gather(const float* volume, int X, int Y, int Z, int c, const int64_t* coords, int64_t K, float* out,
+                     int* bad_rows, void* stream);
+
+/* dst = src + add3 on (M,3) int64 rows (gru_fusion.py:135) */
+int d3m_coords_add(const int64_t* src, int64_t M, const int64_t* add3_host, int64_t* dst, void* stream);
 
 #ifdef __cplusplus
 }

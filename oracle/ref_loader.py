@@ -83,3 +83,76 @@ def integrate_cpu(vol, depth_im, cam_intr, cam_pose, obs_weight=1.0):
         vol.integrate(None, depth_im, cam_intr, cam_pose, obs_weight)
     except IndexError:
         pass
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# the UNMODIFIED `NeuConNet` (models/neucon_network.py) and `GRUFusion`
+# (models/modulars/gru_fusion.py) classes, loaded by path.  Their imports of torchsparse / loguru / the package's
+# own __init__ chain (addict, yapf, trimesh, skimage, cv2 -- none installed) are satisfied by stub modules; the
+# `sparse_to_dense_*` helpers are the reference's own function definitions, taken out of neucon_utils.py's AST
+# because that module's top-level imports cannot be satisfied.
+# ---------------------------------------------------------------------------------------------------------------
+class PointTensorStub:
+    """Stands in for torchsparse.tensor.PointTensor: a (features F, coordinates C) pair."""
+
+    def __init__(self, F, C):
+        self.F, self.C = F, C
+
+    def cuda(self):
+        return self
+
+    def detach(self):
+        return PointTensorStub(self.F.detach(), self.C)
+
+
+class _Quiet:
+    def warning(self, *a, **k):
+        pass
+
+    info = debug = error = warning
+
+
+_neucon = None
+
+
+def neucon_modules():
+    """-> (neucon_network module, gru_fusion module) of the reference."""
+    global _neucon
+    if _neucon is not None:
+        return _neucon
+    import ast
+
+    import torch
+
+    def stub(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        sys.modules[name] = m
+        return m
+
+    def load(rel, name):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REF_ROOT, rel))
+        mod = importlib.util.module_from_spec(spec)
+        sys.modules[name] = mod
+        spec.loader.exec_module(mod)
+        return mod
+
+    stub("torchsparse")
+    stub("torchsparse.tensor", PointTensor=PointTensorStub)
+    stub("loguru", logger=_Quiet())
+    for n in ("deep3dmap", "deep3dmap.models", "deep3dmap.models.modulars", "deep3dmap.core", "deep3dmap.core.utils",
+              "deep3dmap.core.voxel"):
+        stub(n).__path__ = []
+    stub("deep3dmap.models.modulars.sparse_cnn", SPVCNN=object, ConvGRU=object)
+    names = ("sparse_to_dense_torch", "sparse_to_dense_channel", "sparse_to_dense_torch_batch", "apply_log_transform")
+    tree = ast.parse(open(os.path.join(REF_ROOT, "deep3dmap/core/utils/neucon_utils.py")).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "neucon_utils.py", "exec"), ns)
+    stub("deep3dmap.core.utils.neucon_utils", **{k: ns[k] for k in names})
+    load("deep3dmap/core/voxel/back_project.py", "deep3dmap.core.voxel.back_project")
+    load("deep3dmap/core/voxel/generate_grids.py", "deep3dmap.core.voxel.generate_grids")
+    gf = load("deep3dmap/models/modulars/gru_fusion.py", "deep3dmap.models.modulars.gru_fusion")
+    nn_ = load("deep3dmap/models/neucon_network.py", "deep3dmap.models.neucon_network")
+    _neucon = (nn_, gf)
+    return _neucon
