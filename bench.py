@@ -256,6 +256,14 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.legs == "glue":
+        # quick pass over the f2 / f3 legs only (development and `ncu` target); one JSON line
+        out = {"level_glue": {"fragment_x1": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 1),
+                              "fragments_x64": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 64, reps=3)},
+               "gru_fusion": bench_gru_fusion(torch, dev, _lib, flush_buf, peak_gbs)}
+        if rank == 0:
+            emit_json(out)
+        return
     if args.profile_step in ("dense", "tsdf"):
         # profiler targets (`ncu --profile-from-start off`): only the call between cudaProfilerStart/Stop is captured
         if args.profile_step == "tsdf":
@@ -318,9 +326,13 @@ def run_ours(args, rank, world, local_rank):
     # host-side issue cost of one eager step (python + autograd + ctypes + launches), GPU idle at start
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(5):
+    for _ in range(3):
         step_resident()
-    host_ms = (time.perf_counter() - t0) / 5 * 1e3
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(50):
+        step_resident()
+    host_ms = (time.perf_counter() - t0) / 50 * 1e3
     torch.cuda.synchronize()
 
     # ---- timed region 2 (e2e): host buffers in, host buffers out, through the public API ------------
@@ -338,13 +350,15 @@ def run_ours(args, rank, world, local_rank):
         d2h += sum(hp[k].numel() * hp[k].element_size() for k in ("o_vol", "o_cnt", "o_grad"))
         pin.append(hp)
 
-    # one stream per level: the H2D copy of one level, the kernels of another and the D2H copy of a third overlap
-    # (PCIe is full duplex); the levels are independent calls of the public API
+    # one stream per level, issued in two phases (largest level first): every level's forward inputs, forward and
+    # volume/count read-back, then every level's grad_out, backward and grad_feats read-back -- so that the D2H engine
+    # starts as early as possible and stays busy while the H2D engine is still feeding the later levels (PCIe is full
+    # duplex: 55 GB/s one way, 2 x 46 GB/s both ways on this box).  tools/e2e_variants.py compares the issue orders.
     e2e_streams = [torch.cuda.Stream(device=dev) for _ in pin]
 
     def step_e2e():
         main = torch.cuda.current_stream()
-        # largest level first: its D2H then overlaps the H2D of the smaller ones (copy engines are FIFO per direction)
+        keep = []
         for hp, st in reversed(list(zip(pin, e2e_streams))):
             st.wait_stream(main)
             with torch.cuda.stream(st):
@@ -352,10 +366,13 @@ def run_ours(args, rank, world, local_rank):
                 o = hp["origin"].to(dev, non_blocking=True)
                 f = hp["feats"].to(dev, non_blocking=True).requires_grad_(True)
                 k = hp["KRcam"].to(dev, non_blocking=True)
-                g = hp["grad_out"].to(dev, non_blocking=True)
                 vol, cnt = back_project(c, o, hp["vs"], f, k)
                 hp["o_vol"].copy_(vol.detach(), non_blocking=True)
                 hp["o_cnt"].copy_(cnt, non_blocking=True)
+            keep.append((hp, st, vol, f))
+        for hp, st, vol, f in keep:
+            with torch.cuda.stream(st):
+                g = hp["grad_out"].to(dev, non_blocking=True)
                 vol.backward(g)
                 hp["o_grad"].copy_(f.grad, non_blocking=True)
         for st in e2e_streams:
@@ -413,6 +430,17 @@ def run_ours(args, rank, world, local_rank):
     tsdf = None
     if rank == 0:
         tsdf = bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, with_cpu=(world == 1))
+
+    # ---- SURVEY §8 rows f2 / f3 (rank 0 only): level glue around back_project, GRU-fusion volume movement ----
+    glue = fus = None
+    if rank == 0:
+        try:
+            glue = {"fragment_x1": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 1),
+                    "fragments_x64": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 64, reps=3)}
+            fus = bench_gru_fusion(torch, dev, _lib, flush_buf, peak_gbs)
+        except Exception as err:  # secondary legs never take the headline line down
+            log("glue/fusion leg failed:", repr(err))
+            glue = glue or {"error": repr(err)[:300]}
 
     # ---- aggregate ---------------------------------------------------------------------------------------
     if world > 1:
@@ -476,8 +504,9 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": ms_e2e, "what": "back_project() public API from pinned host tensors; volume, count and "
-                "grad_feats copied back to pinned host memory every step; one CUDA stream per level so that H2D, "
-                "kernels and D2H of different levels overlap"},
+                "grad_feats copied back to pinned host memory every step; one CUDA stream per level, forward phase of all "
+                "levels issued before the backward phase, so that H2D, kernels and D2H overlap (PCIe-bound: the step "
+                "moves 51 MB in and 47 MB out)"},
         "gpu_launches": int(launches), "host_issue_ms_per_step": host_ms,
         "step_mode": "cuda_graph_replay" if ms_graph is not None else "eager", "ms_per_step_eager": ms_eager,
         "ms_per_step_graph": ms_graph, "graph_error": graph_err,
@@ -497,6 +526,8 @@ def run_ours(args, rank, world, local_rank):
         "batched_fragments": batched,
         "large_scene": scene,
         "tsdf": tsdf,
+        "level_glue": glue,
+        "gru_fusion": fus,
     }
     emit_json(line)
     if world > 1:
@@ -705,6 +736,196 @@ def bench_dense_l2(torch, dev, _lib, back_project, flush_buf, peak_gbs, steps, p
             "bp_bwd_gather_GBs": (16 * C * S + 4 * V * B * C * H * W + 16 * S) / (gat_ms * 1e-3) / 1e9 if gat_ms else None}
 
 
+def bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, bs, reps=5):
+    """SURVEY §8 row f2 measured: the steps either side of back_project for the three coarse-to-fine levels of `bs`
+    fragments (neucon_network.py:113-207) -- grid / upsample, aligned-camera coords, GT look-up, occupancy
+    thresholding + ordered compaction + TRAIN_NUM_SAMPLE subsampling + the fused gather/concat -- at NeuralRecon's
+    widths (sparse-conv outputs 96/48/24, caps 4096/16384/65536 per fragment).  The network heads (feat/tsdf/occ) and
+    back_project's count are synthetic device tensors.  bs=1 is the headline fragment (launch-latency bound: every
+    kernel moves < 30 MB); bs=64 is the batched-training shape of BASELINE configs[3] (HBM-bound)."""
+    from deep3dmap_b200 import grids
+    n_vox, vs = [96, 96, 96], 0.04
+    ch_out, caps = [96, 48, 24], [4096, 16384, 65536]
+    g = torch.Generator(device=dev).manual_seed(11)
+    origin = torch.zeros((bs, 3), device=dev)
+    w2ac = torch.eye(4, device=dev).repeat(bs, 1, 1).contiguous()
+    w2ac[:, :3, 3] = 0.25
+    tsdf_vol = [torch.rand((bs, 96 >> s, 96 >> s, 96 >> s), device=dev, generator=g) * 2 - 1 for s in range(3)]
+    occ_vol = [t.abs() < 0.5 for t in tsdf_vol]
+
+    def heads(N, i):
+        return (torch.randn((N, ch_out[i]), device=dev, generator=g), torch.randn((N, 1), device=dev, generator=g),
+                torch.randn((N, 1), device=dev, generator=g), torch.randint(0, 10, (N,), device=dev, generator=g).float())
+
+    # fixed head tensors per level (sizes are deterministic because the caps bind: > cap survivors at every level)
+    rng = np.random.default_rng(3)
+    state = {}
+
+    def chain(record=None):
+        pre_feat = pre_coords = None
+        rows = []
+        for i in range(3):
+            scale = 2 - i
+            interval = 2 ** scale
+            if i == 0:
+                up_coords = grids.fragment_grid_coords(n_vox, interval, bs, device=dev)
+            else:
+                up_feat, up_coords = grids.upsample(pre_feat, pre_coords, interval)
+            N = up_coords.shape[0]
+            if i not in state:
+                state[i] = heads(N, i)
+            feat, tsdf, occ, count = state[i]
+            r = grids.aligned_camera_coords(up_coords, origin, vs, w2ac)
+            tt, ot = grids.get_target(up_coords, tsdf_vol[scale], occ_vol[scale], scale, check=False)
+            sel = grids.select_occupied(up_coords, feat, tsdf, occ, None, 0.0, caps[i] * bs, rng=rng, count=count)
+            pre_coords, pre_feat = sel["pre_coords"], sel["pre_feat"]
+            rows.append((N, sel["num"], pre_coords.shape[0], up_coords.element_size() * 4))
+        return rows
+
+    for _ in range(2):
+        rows = chain()
+    torch.cuda.synchronize()
+    # algorithmic bytes per kernel family from the shapes of this chain
+    alg = {}
+    for i, (N, num, kept, cb) in enumerate(rows):
+        C = ch_out[i]
+        def add(k, b):
+            alg[k] = alg.get(k, 0) + int(b)
+        if i == 0:
+            add("grid_coords", 16 * N)
+        else:
+            c_pre = ch_out[i - 1] + 2
+            add("upsample_coords", cb * (N // 8) + cb * N)
+            add("upsample_feat", 4 * c_pre * (N // 8) + 4 * c_pre * N)
+        add("aligned_camera_coords", cb * N + 16 * N)
+        add("gather_targets", cb * N + 5 * N + 5 * N)
+        add("occupancy_flags", 4 * N + 4 * N + N)
+        add("compact_count", N + (kept if num > kept else 0))
+        add("compact_write", N + 8 * num + ((num + 8 * num + 8 * kept) if num > kept else 0))
+        if num > kept:
+            add("drop_ranks", 8 * (num - kept) + num)
+        add("gather_rows", kept * (8 + 2 * cb))
+        add("gather_concat", kept * (8 + 2 * 4 * (C + 2)))
+    ev, wall, acc = [], [], {}
+    for _ in range(reps):
+        flush_buf.fill_(1)
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record(); chain(); b.record()
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e3)
+        ev.append(a.elapsed_time(b))
+    l0 = _lib.kernel_launches()
+    for _ in range(reps):
+        flush_buf.fill_(1)
+        torch.cuda.synchronize()
+        _lib.profile_begin()
+        chain()
+        for k, v in _lib.profile_end().items():
+            e = acc.setdefault(k, {"n": 0, "ms": 0.0})
+            e["n"] += v["n"]; e["ms"] += v["ms"]
+    launches = (_lib.kernel_launches() - l0) // reps
+    kern_ms = {k: v["ms"] / reps for k, v in acc.items()}
+    t_kern = sum(kern_ms.values())
+    a_total = sum(alg.values())
+    per_kernel = {}
+    for k in sorted(kern_ms):
+        b = alg.get(k)
+        per_kernel[k] = {"us": round(kern_ms[k] * 1e3, 2), "launches": acc[k]["n"] // reps,
+                         "algorithmic_MB": round(b / 1e6, 3) if b else None,
+                         "GBs": round(b / (kern_ms[k] * 1e-3) / 1e9, 1) if b and kern_ms[k] > 0 else None}
+    dom = max(kern_ms, key=kern_ms.get)
+    rows_total = sum(r[0] for r in rows)
+    return {"fragments": bs, "rows_per_level": [r[0] for r in rows], "survivors_per_level": [r[1] for r in rows],
+            "kept_per_level": [r[2] for r in rows], "unit": "voxel rows/s", "rows_per_s": rows_total / (float(np.mean(ev)) * 1e-3),
+            "ms_chain_device": float(np.mean(ev)), "ms_chain_wall": float(np.mean(wall)), "ms_kernels_sum": t_kern,
+            "gpu_launches": int(launches), "algorithmic_bytes": int(a_total),
+            "roofline": {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["GBs"], "peak": peak_gbs, "unit": "GB/s",
+                         "frac": (per_kernel[dom]["GBs"] or 0.0) / peak_gbs,
+                         "all_kernels_achieved": a_total / (t_kern * 1e-3) / 1e9 if t_kern else None,
+                         "all_kernels_frac": a_total / (t_kern * 1e-3) / 1e9 / peak_gbs if t_kern else None},
+            "kernels": per_kernel,
+            "note": "host read-backs (survivor count, np.random.choice of the surplus like neucon_network.py:184-194) are "
+                    "inside ms_chain_wall and ms_chain_device; ms_kernels_sum is device time of the kernels alone"}
+
+
+def bench_gru_fusion(torch, dev, _lib, flush_buf, peak_gbs, reps=6):
+    """SURVEY §8 row f3 measured: GRUFusion.forward at the finest scale (96^3 fragment bounding volume, 24 hidden
+    channels, FUSION.FULL) for a camera walking through one scene -- sparse -> dense of the global and the current
+    volume, union of the sparsity, dense -> sparse, map update -- and the direct-substitute TSDF fuse with save_mesh.
+    The ConvGRU (torchsparse, out of scope) is replaced by `lambda h, x, r: x` (no kernel)."""
+    from types import SimpleNamespace
+    from deep3dmap_b200 import fusion
+    n = 96
+    cfg = SimpleNamespace(N_LAYER=3, N_VOX=[n, n, n], VOXEL_SIZE=0.04, THRESHOLDS=[0, 0, 0],
+                          FUSION=SimpleNamespace(FUSION_ON=True, FULL=True))
+    rng = np.random.default_rng(17)
+    ax = np.arange(n)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    res = {}
+    for mode, c in (("gru_full_c24", 24), ("direct_substitute_tsdf", 1)):
+        direct = c == 1
+        fz = fusion.GRUFusion(cfg, ch_in=[96, 48, 24], direct_substitute=direct,
+                              fusion_nets=None if direct else [None, None, (lambda h, x, r: x)], device=dev)
+        steps = []
+        for k in range(reps + 2):
+            # a wavy surface sheet, ~2 voxels thick, different in every fragment: ~ 20 k occupied voxels of 96^3
+            surf = 48 + 20 * np.sin((X + 13 * k) / 17.0) * np.cos(Y / 23.0)
+            pick = np.flatnonzero(np.abs(Z - surf) < 1.2)
+            xyz = np.stack(np.unravel_index(pick, (n, n, n)), 1).astype(np.int64)
+            coords = np.concatenate([np.zeros((len(pick), 1), np.int64), xyz], 1)
+            vals = rng.uniform(-0.9, 0.9, (len(pick), c)).astype(np.float32) if direct else rng.standard_normal((len(pick), c)).astype(np.float32)
+            shift = np.array([24 * k, 3 * k, 0], np.float32) * 0.04
+            inputs = dict(img_metas=[{"scene": "s"}], vol_origin=torch.zeros((1, 3), device=dev),
+                          vol_origin_partial=torch.from_numpy(shift[None]).to(dev),
+                          world_to_aligned_camera=torch.eye(4, device=dev)[None].contiguous())
+            steps.append((torch.from_numpy(coords).to(dev), torch.from_numpy(vals).to(dev), inputs))
+        outputs = None
+        ts, rows, acc = [], [], {}
+        l0 = None
+        for k, (co, va, inp) in enumerate(steps):
+            flush_buf.fill_(1)
+            torch.cuda.synchronize()
+            if k >= 2:
+                if l0 is None:
+                    l0 = _lib.kernel_launches()
+                _lib.profile_begin()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            ret = fz.forward(co, va, inp, scale=2, outputs=outputs, save_mesh=direct)
+            b.record()
+            torch.cuda.synchronize()
+            if direct:
+                outputs = ret
+            if k >= 2:
+                for kk, v in _lib.profile_end().items():
+                    e = acc.setdefault(kk, {"n": 0, "ms": 0.0})
+                    e["n"] += v["n"]; e["ms"] += v["ms"]
+                ts.append(a.elapsed_time(b))
+                rows.append(int(co.shape[0]))
+        launches = (_lib.kernel_launches() - l0) // reps
+        kern_ms = {k: v["ms"] / reps for k, v in acc.items()}
+        t_kern = sum(kern_ms.values())
+        vol_bytes = n * n * n * c * 4
+        m_glob = int(fz.global_volume[2].C.shape[0])
+        K = float(np.mean(rows))
+        # dense fill of global + current volume, both read by the union pass, scattered rows in, gathered rows out x2
+        a_bytes = 2 * vol_bytes + 2 * vol_bytes + int(K) * (24 + 4 * c) * 2 + 2 * int(K) * (24 + 4 * c)
+        dom = max(kern_ms, key=kern_ms.get)
+        res[mode] = {"fragment_volume": "96^3 x %d ch" % c, "rows_in_per_call": int(K), "global_map_rows_end": m_glob,
+                     "ms_per_forward": float(np.mean(ts)), "ms_kernels_sum": t_kern, "gpu_launches_per_forward": int(launches),
+                     "fragments_per_s": 1e3 / float(np.mean(ts)),
+                     "algorithmic_bytes_per_forward": int(a_bytes),
+                     "roofline": {"bound": "hbm", "kernel": dom, "achieved": a_bytes / (t_kern * 1e-3) / 1e9 if t_kern else None,
+                                  "peak": peak_gbs, "unit": "GB/s",
+                                  "frac": a_bytes / (t_kern * 1e-3) / 1e9 / peak_gbs if t_kern else None,
+                                  "what": "all fusion kernels of one forward: 2 dense fills + union pass over both volumes "
+                                          "+ scattered / gathered rows"},
+                     "kernel_us": {k: round(v * 1e3, 2) for k, v in sorted(kern_ms.items())}}
+    return res
+
+
 def bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=False, with_cpu=True):
     """BASELINE configs[2]: 300 synthetic 640x480 depth frames into a 512^3 volume at 4 cm."""
     F = N_TSDF_FRAMES
@@ -819,6 +1040,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time the eager python path only")
+    ap.add_argument("--legs", default="all", choices=["all", "glue"], help="'glue': only the level-glue / GRU-fusion legs")
     ap.add_argument("--profile-step", default="", choices=["", "bp", "tsdf", "dense"],
                     help="profiler target: run only the hot-path steps (and the TSDF launches with 'tsdf'), print nothing")
     args = ap.parse_args()

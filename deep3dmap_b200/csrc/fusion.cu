@@ -81,20 +81,71 @@ __global__ void __launch_bounds__(256) fbv_mask_kernel(const int64_t* __restrict
 // sparsity of the fused fragment (gru_fusion.py:100-106):
 //   mode 0:  (a != 0).any(-1) | (b != 0).any(-1)          feature volumes (default 0)
 //   mode 1:  (|a| < 1).any(-1) | (|b| < 1).any(-1)        tsdf volumes (default 1)
+__device__ __forceinline__ bool union_pred(float v, int mode) { return mode ? fabsf(v) < 1.0f : v != 0.0f; }
+
+// c == 1 (tsdf volumes) and the generic fallback: one thread per voxel
 __global__ void __launch_bounds__(256) union_flags_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                           int64_t n_vox, int c, int mode, uint8_t* __restrict__ flags) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_vox) return;
   bool f = false;
   for (int j = 0; j < c; ++j) {
-    const float va = __ldg(a + i * c + j);
-    f = f || (mode ? fabsf(va) < 1.0f : va != 0.0f);
-    if (b) {
-      const float vb = __ldg(b + i * c + j);
-      f = f || (mode ? fabsf(vb) < 1.0f : vb != 0.0f);
-    }
+    f = f || union_pred(__ldg(a + i * c + j), mode);
+    if (b) f = f || union_pred(__ldg(b + i * c + j), mode);
   }
   flags[i] = f ? 1 : 0;
+}
+
+// c > 1: a warp owns 32 consecutive voxels = one contiguous span of 32*c floats of each volume and reads it with
+// fully coalesced VecT loads (W = c / floats-per-VecT iterations, lane l takes unit k*32+l); the predicate of every
+// unit goes through a ballot into a W-word bitmap per warp, and lane v then ORs the W bits of voxel v.  The
+// thread-per-voxel version strode through memory 4*c bytes apart and reached 20 % of the HBM peak.
+constexpr int UF_MAX_W = 64;
+template <typename VecT>
+__global__ void __launch_bounds__(256) union_flags_warp_kernel(const VecT* __restrict__ a, const VecT* __restrict__ b,
+                                                               int64_t n_vox, int W, int mode,
+                                                               uint8_t* __restrict__ flags) {
+  __shared__ unsigned bits[8][UF_MAX_W];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int64_t v0 = ((int64_t)blockIdx.x * 8 + wid) * 32;
+  if (v0 >= n_vox) return;
+  const int nv = (int)min((int64_t)32, n_vox - v0);
+  const int n_units = nv * W;
+  const VecT* pa = a + v0 * W;
+  const VecT* pb = b ? b + v0 * W : nullptr;
+#pragma unroll 4
+  for (int k = 0; k < W; ++k) {
+    const int u = k * 32 + lane;
+    bool f = false;
+    if (u < n_units) {
+      const VecT x = __ldcs(pa + u);
+      const float* xf = reinterpret_cast<const float*>(&x);
+#pragma unroll
+      for (int q = 0; q < (int)(sizeof(VecT) / 4); ++q) f = f || union_pred(xf[q], mode);
+      if (pb) {
+        const VecT y = __ldcs(pb + u);
+        const float* yf = reinterpret_cast<const float*>(&y);
+#pragma unroll
+        for (int q = 0; q < (int)(sizeof(VecT) / 4); ++q) f = f || union_pred(yf[q], mode);
+      }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    if (lane == 0) bits[wid][k] = m;
+  }
+  __syncwarp();
+  if (lane < nv) {
+    // bits [lane*W, lane*W + W) of the concatenated bitmap
+    const int lo = lane * W, hi = lo + W;
+    unsigned any = 0;
+    for (int w = lo >> 5; w <= (hi - 1) >> 5; ++w) {
+      unsigned m = bits[wid][w];
+      const int b0 = w << 5;
+      if (lo > b0) m &= 0xffffffffu << (lo - b0);
+      if (hi < b0 + 32) m &= (1u << (hi - b0)) - 1u;
+      any |= m;
+    }
+    flags[v0 + lane] = any ? 1 : 0;
+  }
 }
 
 // linear voxel index -> (x,y,z) [+ offset] rows, optionally with a leading batch column and a scale on xyz
@@ -210,7 +261,15 @@ extern "C" int d3m_dense_union_flags(const float* vol_a, const float* vol_b, int
   D3M_REQUIRE(vol_a && flags, D3M_ERR_ARG, "d3m_dense_union_flags: NULL pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LaunchScope ls("dense_union_flags", stream);
-  union_flags_kernel<<<nblocks(n_vox, 256), 256, 0, stream>>>(vol_a, vol_b, n_vox, c, mode, flags);
+  const uintptr_t al = reinterpret_cast<uintptr_t>(vol_a) | reinterpret_cast<uintptr_t>(vol_b);
+  if (c > 1 && c % 4 == 0 && c / 4 <= UF_MAX_W && (al & 15u) == 0) {
+    union_flags_warp_kernel<float4><<<nblocks(n_vox, 256), 256, 0, stream>>>(
+        reinterpret_cast<const float4*>(vol_a), reinterpret_cast<const float4*>(vol_b), n_vox, c / 4, mode, flags);
+  } else if (c > 1 && c <= UF_MAX_W) {
+    union_flags_warp_kernel<float><<<nblocks(n_vox, 256), 256, 0, stream>>>(vol_a, vol_b, n_vox, c, mode, flags);
+  } else {
+    union_flags_kernel<<<nblocks(n_vox, 256), 256, 0, stream>>>(vol_a, vol_b, n_vox, c, mode, flags);
+  }
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
 }

@@ -77,27 +77,34 @@ __global__ void __launch_bounds__(256) upsample_coords_kernel(const void* __rest
   }
 }
 
-// up_feat = pre_feat.unsqueeze(1).expand(-1,num,-1): every input row becomes a contiguous span of num*C floats.
-// VEC=4: one 128-bit store per thread (span start is 16-byte aligned when num*C % 4 == 0); reads hit L1.
-template <int VEC>
-__global__ void __launch_bounds__(256) upsample_feat_kernel(const float* __restrict__ pre, int64_t total_vec, int C,
-                                                            int span /* num*C */, float* __restrict__ up) {
-  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// up_feat = pre_feat.unsqueeze(1).expand(-1,num,-1): every input row is written `num` times, back to back.
+// One thread = one VecT (128 / 64 / 32 bit, the widest that divides the row and the pointers' alignment) of one INPUT
+// row: loaded once, stored to the `num` children rows -- consecutive lanes cover consecutive vectors of a row, so every
+// store instruction of a warp writes whole 128-byte lines of one or two output rows.  IdxT = uint32 whenever the vector
+// count fits (64-bit division costs ~100 instructions per thread).
+template <typename VecT, typename IdxT>
+__global__ void __launch_bounds__(256) upsample_feat_kernel(const VecT* __restrict__ pre, IdxT total_vec, IdxT vec_per_row,
+                                                            int num, VecT* __restrict__ up) {
+  const IdxT t = (IdxT)blockIdx.x * (IdxT)blockDim.x + threadIdx.x;
   if (t >= total_vec) return;
-  const int64_t o = t * VEC;
-  const int64_t n = o / span;
-  int j = (int)(o - n * span) % C;
-  const float* row = pre + n * C;
-  if (VEC == 4) {
-    float v[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      v[k] = __ldg(row + j);
-      j = (j + 1 == C) ? 0 : j + 1;
-    }
-    reinterpret_cast<float4*>(up)[t] = make_float4(v[0], v[1], v[2], v[3]);
+  const IdxT n = t / vec_per_row;
+  const IdxT j = t - n * vec_per_row;
+  const VecT v = __ldg(pre + t);
+  VecT* o = up + ((int64_t)n * num) * vec_per_row + j;
+#pragma unroll 8
+  for (int i = 0; i < num; ++i) __stcs(o + (int64_t)i * vec_per_row, v);
+}
+
+template <typename VecT>
+static void launch_upsample_feat(const float* pre, int64_t N, int C, int num, float* up, cudaStream_t stream) {
+  const int per = (int)(sizeof(VecT) / 4);
+  const int64_t vpr = C / per, total = N * vpr;
+  if (total < (1ll << 32)) {
+    upsample_feat_kernel<VecT, uint32_t><<<blocks_for(total, 256), 256, 0, stream>>>(
+        reinterpret_cast<const VecT*>(pre), (uint32_t)total, (uint32_t)vpr, num, reinterpret_cast<VecT*>(up));
   } else {
-    up[o] = __ldg(row + j);
+    upsample_feat_kernel<VecT, uint64_t><<<blocks_for(total, 256), 256, 0, stream>>>(
+        reinterpret_cast<const VecT*>(pre), (uint64_t)total, (uint64_t)vpr, num, reinterpret_cast<VecT*>(up));
   }
 }
 
@@ -356,6 +363,7 @@ struct ConcatSrc {
   int n;
 };
 
+// Generic path (any widths / alignment): one thread per output float.
 __global__ void __launch_bounds__(256) gather_concat_kernel(ConcatSrc s, const int64_t* __restrict__ ind,
                                                             int64_t total, float* __restrict__ dst) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -369,6 +377,100 @@ __global__ void __launch_bounds__(256) gather_concat_kernel(ConcatSrc s, const i
   for (int q = 1; q < 4; ++q)
     if (q < s.n && col >= s.begin[q]) k = q;
   dst[t] = __ldg(s.p[k] + r * s.w[k] + (col - s.begin[k]));
+}
+
+// Pair path (even row width, 8-byte aligned destination -- the NeuralRecon case: C + 2 floats with C = 96/48/24):
+// one thread = GC_UNROLL 64-bit units of the flat output; a unit never straddles a row because the width is even.
+// Units that lie inside one even-aligned source are fetched with one 64-bit load, the (tsdf, occ) tail pair with two
+// 32-bit loads.  No shared memory, no barrier: all of a thread's loads are in flight before its first store, and a
+// warp's stores are one contiguous 256-byte span.
+constexpr int GC_UNROLL = 4;
+__global__ void __launch_bounds__(256) gather_concat_pair_kernel(ConcatSrc s, const int64_t* __restrict__ ind,
+                                                                 uint32_t total_units, uint32_t units_per_row,
+                                                                 float2* __restrict__ dst) {
+  const uint32_t t0 = (blockIdx.x * (uint32_t)blockDim.x * GC_UNROLL) + threadIdx.x;
+  float2 v[GC_UNROLL];
+#pragma unroll
+  for (int q = 0; q < GC_UNROLL; ++q) {
+    const uint32_t t = t0 + q * blockDim.x;
+    v[q] = make_float2(0.f, 0.f);
+    if (t < total_units) {
+      const uint32_t m = t / units_per_row;
+      const int col = (int)(t - m * units_per_row) * 2;
+      const int64_t r = ind ? __ldg(ind + m) : (int64_t)m;
+      int k = 0;
+#pragma unroll
+      for (int j = 1; j < 4; ++j)
+        if (j < s.n && col >= s.begin[j]) k = j;
+      const int c0 = col - s.begin[k];
+      const float* p0 = s.p[k] + r * s.w[k] + c0;
+      if (c0 + 1 < s.w[k]) {
+        if ((reinterpret_cast<uintptr_t>(p0) & 7u) == 0) {
+          v[q] = __ldg(reinterpret_cast<const float2*>(p0));
+        } else {
+          v[q] = make_float2(__ldg(p0), __ldg(p0 + 1));
+        }
+      } else {
+        int k1 = k + 1;
+        while (k1 < s.n - 1 && s.w[k1] == 0) ++k1;   // col+1 < row width, so a non-empty source follows
+        v[q] = make_float2(__ldg(p0), __ldg(s.p[k1] + r * s.w[k1]));
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < GC_UNROLL; ++q) {
+    const uint32_t t = t0 + q * blockDim.x;
+    if (t < total_units) __stcs(dst + t, v[q]);
+  }
+}
+
+// Tiled path: a CTA assembles GC_ROWS consecutive OUTPUT rows in shared memory -- every source row is fetched with the
+// widest vector its width and base alignment allow (128-bit for the 24/48/96-float feature rows), the index is read
+// once per row -- and then streams the tile, which is one contiguous span of GC_ROWS*wtot floats starting on a
+// 128-byte boundary, to global memory with 128-bit stores.  Output rows are C+2 floats wide (not a multiple of 16
+// bytes), which is why a direct row-wise vector store is impossible and the one-float-per-thread version ran at 13 %
+// of the HBM peak.
+constexpr int GC_ROWS = 32;
+__global__ void __launch_bounds__(256) gather_concat_tile_kernel(ConcatSrc s, const int64_t* __restrict__ ind, int64_t M,
+                                                                 float* __restrict__ dst) {
+  extern __shared__ __align__(16) float gc_tile[];
+  __shared__ int64_t rows[GC_ROWS];
+  const int wtot = s.begin[s.n];
+  const int64_t m0 = (int64_t)blockIdx.x * GC_ROWS;
+  const int nrow = (int)min((int64_t)GC_ROWS, M - m0);
+  if (threadIdx.x < nrow) rows[threadIdx.x] = ind ? __ldg(ind + m0 + threadIdx.x) : m0 + threadIdx.x;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    if (k >= s.n || s.w[k] == 0) continue;
+    const int w = s.w[k];
+    const float* __restrict__ src = s.p[k];
+    if ((w & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+      const int vpr = w >> 2;
+      for (int t = threadIdx.x; t < nrow * vpr; t += blockDim.x) {
+        const int r = t / vpr, j = t - r * vpr;
+        const float4 v = __ldg(reinterpret_cast<const float4*>(src + rows[r] * w) + j);
+        float* o = gc_tile + r * wtot + s.begin[k] + 4 * j;
+        o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+      }
+    } else {
+      for (int t = threadIdx.x; t < nrow * w; t += blockDim.x) {
+        const int r = t / w, j = t - r * w;
+        gc_tile[r * wtot + s.begin[k] + j] = __ldg(src + rows[r] * w + j);
+      }
+    }
+  }
+  __syncthreads();
+  float* out = dst + m0 * wtot;
+  const int nflt = nrow * wtot;
+  if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0) {
+    const int nvec = nflt >> 2;
+    for (int t = threadIdx.x; t < nvec; t += blockDim.x)
+      __stcs(reinterpret_cast<float4*>(out) + t, reinterpret_cast<const float4*>(gc_tile)[t]);
+    for (int t = (nvec << 2) + threadIdx.x; t < nflt; t += blockDim.x) out[t] = gc_tile[t];
+  } else {
+    for (int t = threadIdx.x; t < nflt; t += blockDim.x) out[t] = gc_tile[t];
+  }
 }
 
 // number of rows per fragment (neucon_network.py:197-201 "no valid points: scale, batch")
@@ -450,13 +552,14 @@ extern "C" int d3m_upsample(const void* pre_coords, int coords_kind, const float
   }
   if (pre_feat && C > 0) {
     D3M_REQUIRE(up_feat != nullptr, D3M_ERR_ARG, "d3m_upsample: up_feat is NULL");
-    const int span = num * C;
-    const int64_t total = N * span;
     LaunchScope ls("upsample_feat", stream);
-    if (span % 4 == 0 && aligned16(up_feat)) {
-      upsample_feat_kernel<4><<<blocks_for(total / 4, 256), 256, 0, stream>>>(pre_feat, total / 4, C, span, up_feat);
+    const uintptr_t al = reinterpret_cast<uintptr_t>(pre_feat) | reinterpret_cast<uintptr_t>(up_feat);
+    if (C % 4 == 0 && (al & 15u) == 0) {
+      launch_upsample_feat<float4>(pre_feat, N, C, num, up_feat, stream);
+    } else if (C % 2 == 0 && (al & 7u) == 0) {
+      launch_upsample_feat<float2>(pre_feat, N, C, num, up_feat, stream);
     } else {
-      upsample_feat_kernel<1><<<blocks_for(total, 256), 256, 0, stream>>>(pre_feat, total, C, span, up_feat);
+      launch_upsample_feat<float>(pre_feat, N, C, num, up_feat, stream);
     }
     D3M_CUDA_CHECK(cudaGetLastError());
   }
@@ -617,7 +720,17 @@ extern "C" int d3m_gather_concat(const float* const* srcs_host, const int* width
   D3M_REQUIRE(dst != nullptr, D3M_ERR_ARG, "d3m_gather_concat: dst is NULL");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LaunchScope ls("gather_concat", stream);
-  gather_concat_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(s, ind, total, dst);
+  const size_t tile_bytes = (size_t)GC_ROWS * s.begin[n_src] * sizeof(float);
+  const int wtot = s.begin[n_src];
+  if (wtot % 2 == 0 && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0 && total / 2 < (1ll << 32) - (1 << 20)) {
+    const int64_t units = total / 2;
+    gather_concat_pair_kernel<<<blocks_for(units, 256 * GC_UNROLL), 256, 0, stream>>>(
+        s, ind, (uint32_t)units, (uint32_t)(wtot / 2), reinterpret_cast<float2*>(dst));
+  } else if (tile_bytes <= 40 * 1024) {
+    gather_concat_tile_kernel<<<blocks_for(M, GC_ROWS), 256, tile_bytes, stream>>>(s, ind, M, dst);
+  } else {
+    gather_concat_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(s, ind, total, dst);
+  }
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
 }
