@@ -260,7 +260,8 @@ def run_ours(args, rank, world, local_rank):
         # quick pass over the f2 / f3 legs only (development and `ncu` target); one JSON line
         out = {"level_glue": {"fragment_x1": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 1),
                               "fragments_x64": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 64, reps=3)},
-               "gru_fusion": bench_gru_fusion(torch, dev, _lib, flush_buf, peak_gbs)}
+               "gru_fusion": bench_gru_fusion(torch, dev, _lib, flush_buf, peak_gbs),
+               "gt_transform": bench_gt_transform(torch, dev, _lib, flush_buf, peak_gbs)}
         if rank == 0:
             emit_json(out)
         return
@@ -432,12 +433,13 @@ def run_ours(args, rank, world, local_rank):
         tsdf = bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, with_cpu=(world == 1))
 
     # ---- SURVEY §8 rows f2 / f3 (rank 0 only): level glue around back_project, GRU-fusion volume movement ----
-    glue = fus = None
+    glue = fus = gtt = None
     if rank == 0:
         try:
             glue = {"fragment_x1": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 1),
                     "fragments_x64": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 64, reps=3)}
             fus = bench_gru_fusion(torch, dev, _lib, flush_buf, peak_gbs)
+            gtt = bench_gt_transform(torch, dev, _lib, flush_buf, peak_gbs, with_cpu=(world == 1))
         except Exception as err:  # secondary legs never take the headline line down
             log("glue/fusion leg failed:", repr(err))
             glue = glue or {"error": repr(err)[:300]}
@@ -528,6 +530,7 @@ def run_ours(args, rank, world, local_rank):
         "tsdf": tsdf,
         "level_glue": glue,
         "gru_fusion": fus,
+        "gt_transform": gtt,
     }
     emit_json(line)
     if world > 1:
@@ -848,6 +851,97 @@ def bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, bs, reps=5):
             "kernels": per_kernel,
             "note": "host read-backs (survivor count, np.random.choice of the surplus like neucon_network.py:184-194) are "
                     "inside ms_chain_wall and ms_chain_device; ms_kernels_sum is device time of the kernels alone"}
+
+
+def bench_gt_transform(torch, dev, _lib, flush_buf, peak_gbs, reps=5, with_cpu=True):
+    """SURVEY §8 row f1, ground-truth side: one dataloader sample through `SeqRandomTransformSpace` -- 9 views of
+    480x640 depth integrated into the 96^3 / 48^3 / 24^3 fragment volumes (TSDFVolumeTorch semantics, one batched launch
+    per level), occupancy thresholding, and the nearest/trilinear re-crop of a ScanNet-room sized scene TSDF
+    (300 x 260 x 90 voxels at 4 cm and its two coarser levels).  Host tensors in, host tensors out, as in the
+    dataloader; the CPU baseline is the oracle port of the same steps on the host cores."""
+    from deep3dmap_b200.transforms import SeqRandomTransformSpace
+    rng = np.random.default_rng(5)
+    V, H, W = 9, 480, 640
+    vs = 0.04
+    full_dims = [(300 >> l, 260 >> l, 90 >> l) for l in range(3)]
+    full = []
+    for d in full_dims:
+        t = np.clip(rng.standard_normal(d).astype(np.float32) * 0.8, -1, 1)
+        t[rng.random(d) < 0.5] = 1.0
+        full.append(t)
+    K = np.array([[577.87, 0, 319.5], [0, 577.87, 239.5], [0, 0, 1]], dtype=np.float32)
+    poses = []
+    for v in range(V):
+        a = 0.12 * (v - 4)
+        f = np.array([np.cos(0.6 + a), np.sin(0.6 + a), -0.25]); f /= np.linalg.norm(f)
+        r = np.cross(f, [0, 0, 1.0]); r /= np.linalg.norm(r)
+        dn = np.cross(f, r)
+        M = np.eye(4); M[:3, 0], M[:3, 1], M[:3, 2], M[:3, 3] = r, dn, f, [4.0 + 0.15 * v, 3.0, 1.5]
+        poses.append(M.astype(np.float32))
+    u, vv = np.meshgrid(np.arange(W), np.arange(H))
+    depth = np.stack([np.clip(2.0 + 0.5 * np.sin(u / 97.0 + f) + 0.4 * np.cos(vv / 71.0), 0.5, 3.0).astype(np.float32)
+                      for f in range(V)])
+
+    def data_dict():
+        return {"vol_origin": np.array([0.0, 0.0, -0.2], dtype=np.float32), "epoch": [3],
+                "tsdf_list_full": [torch.from_numpy(t) for t in full], "extrinsics": torch.from_numpy(np.stack(poses)).clone(),
+                "intrinsics": torch.from_numpy(np.stack([K] * V)), "imgs": torch.zeros((V, 3, H, W)),
+                "depth": torch.from_numpy(depth)}
+
+    torch.manual_seed(1)
+    tr = SeqRandomTransformSpace([96, 96, 96], vs, max_epoch=8)
+    for _ in range(2):
+        out = tr(data_dict())
+    torch.cuda.synchronize()
+    wall, acc = [], {}
+    l0 = _lib.kernel_launches()
+    for _ in range(reps):
+        d = data_dict()
+        flush_buf.fill_(1)
+        torch.cuda.synchronize()
+        _lib.profile_begin()
+        t0 = time.perf_counter()
+        out = tr(d)
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e3)
+        for k, v in _lib.profile_end().items():
+            e = acc.setdefault(k, {"n": 0, "ms": 0.0})
+            e["n"] += v["n"]; e["ms"] += v["ms"]
+    launches = (_lib.kernel_launches() - l0) // reps
+    kern_us = {k: round(v["ms"] / reps * 1e3, 2) for k, v in sorted(acc.items())}
+    n_out = sum((96 >> l) ** 3 for l in range(3))
+    # recrop: 9 taps (36 B) in + 4 B out per voxel; occupancy: 8 B in + 1 B out
+    alg_crop = n_out * 40
+    crop_ms = acc.get("gt_recrop", {"ms": 0.0})["ms"] / reps
+    res = {"sample": "9 views 480x640 -> 96^3/48^3/24^3 fragment GT; scene tsdf 300x260x90 @ 4 cm (+2 coarser levels)",
+           "ms_per_sample_wall": float(np.mean(wall)), "samples_per_s": 1e3 / float(np.mean(wall)),
+           "ms_kernels_sum": sum(v["ms"] for v in acc.values()) / reps, "gpu_launches_per_sample": int(launches),
+           "h2d_bytes_per_sample": int(depth.nbytes + sum(t.nbytes for t in full)),
+           "d2h_bytes_per_sample": int(n_out * 5), "kernel_us": kern_us,
+           "occupied_voxels": [int(o.sum()) for o in out["occ_list"]],
+           "surface_voxels": [int((t.abs() < 1).sum()) for t in out["tsdf_list"]],
+           "roofline": {"bound": "hbm", "kernel": "gt_recrop", "achieved": alg_crop / (crop_ms * 1e-3) / 1e9 if crop_ms else None,
+                        "peak": peak_gbs, "unit": "GB/s", "frac": alg_crop / (crop_ms * 1e-3) / 1e9 / peak_gbs if crop_ms else None,
+                        "note": "latency-bound: 1.0 M output voxels in three launches; the scene volume (28 MB) is L2-resident"}}
+    if with_cpu:
+        import oracle
+        from oracle import recrop
+        T_inv, origin = tr.world_transform(data_dict())
+        T_inv = T_inv.inverse().numpy()
+        vop = out["vol_origin_partial"].numpy()
+        t0 = time.perf_counter()
+        for l in range(3):
+            dims = [96 >> l] * 3
+            tv = np.ones(dims, np.float32); wv = np.zeros(dims, np.float32)
+            for v in range(V):
+                w2c = np.linalg.inv(np.linalg.inv(T_inv) @ poses[v]).astype(np.float32)   # inverse of the moved pose
+                oracle.tsdf_integrate_torch(tv, wv, vop, vs * 2 ** l, K, w2c, depth[v], 3 * vs * 2 ** l, 1.0)
+            recrop.tsdf_occupancy(tv, wv)
+            recrop.gt_recrop(full[l], [96, 96, 96], vs, vop, T_inv, origin.numpy(), l)
+        cpu_s = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": "samples/s", "cores": oracle.num_threads(), "kind": "port",
+                               "sample": "1 sample: 27 integrations (OpenMP C port) + numpy port of occupancy / re-crop"}
+    return res
 
 
 def bench_gru_fusion(torch, dev, _lib, flush_buf, peak_gbs, reps=6):

@@ -8,7 +8,8 @@ and every compute call raises `D3MError` if it (or a CUDA device) is missing.
 """
 from ._lib import D3MError, LIB_PATH  # noqa: F401
 
-__all__ = ["back_project", "TSDFVolume", "TSDFVolumeTorch", "get_view_frustum", "rigid_transform", "D3MError"]
+__all__ = ["back_project", "TSDFVolume", "TSDFVolumeTorch", "get_view_frustum", "rigid_transform", "D3MError",
+           "SeqRandomTransformSpace"]
 
 
 def __getattr__(name):
@@ -19,4 +20,7 @@ def __getattr__(name):
     if name in ("TSDFVolume", "TSDFVolumeTorch", "get_view_frustum", "rigid_transform"):
         from . import tsdf
         return getattr(tsdf, name)
+    if name == "SeqRandomTransformSpace":
+        from .transforms import SeqRandomTransformSpace
+        return SeqRandomTransformSpace
     raise AttributeError(name)

@@ -17,8 +17,10 @@ SYMBOLS = (
     "d3m_back_project_fwd_workspace", "d3m_back_project_cell_hist_elems", "d3m_back_project_fwd",
     "d3m_back_project_fwd_partial", "d3m_back_project_fwd_finish",
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
-    "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_integrate_host",
+    "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_rebase", "d3m_tsdf_integrate_host",
     "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches",
+    # ground-truth side of the dataloader transform
+    "d3m_tsdf_occupancy", "d3m_gt_recrop",
     # level glue around back_project
     "d3m_grid_coords", "d3m_upsample", "d3m_aligned_camera_coords", "d3m_gather_targets", "d3m_occupancy_flags",
     "d3m_compact_workspace", "d3m_compact", "d3m_drop_ranks", "d3m_gather_rows", "d3m_gather_concat",
@@ -81,6 +83,8 @@ def lib():
     L.d3m_tsdf_destroy.restype = i32
     L.d3m_tsdf_reset.argtypes = [vp, vp]
     L.d3m_tsdf_reset.restype = i32
+    L.d3m_tsdf_rebase.argtypes = [vp, vp, f32, f32, vp]
+    L.d3m_tsdf_rebase.restype = i32
     L.d3m_tsdf_integrate_host.argtypes = [vp, vp, vp, i32, i32, vp, vp, f32, i32, vp]
     L.d3m_tsdf_integrate_host.restype = i32
     L.d3m_tsdf_integrate_device.argtypes = [vp, vp, vp, i32, i32, i32, vp, i32, vp, vp, i32, vp]
@@ -108,6 +112,8 @@ def lib():
         "d3m_unravel_coords": [vp, i64, i32, i32, ctypes.POINTER(i64), i64, i32, i64, vp, vp],
         "d3m_dense_gather": [vp, i32, i32, i32, i32, vp, i64, vp, vp, vp],
         "d3m_coords_add": [vp, i64, ctypes.POINTER(i64), vp, vp],
+        "d3m_tsdf_occupancy": [vp, vp, i64, f32, f32, f32, vp, vp],
+        "d3m_gt_recrop": [vp, i32, i32, i32, i32, i32, i32, i32, f32, vp, vp, vp, vp, vp],
     }
     for name, args in sigs.items():
         f = getattr(L, name)

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["core.cu", "back_project_fwd.cu", "back_project_bwd.cu", "tsdf.cu", "level_glue.cu", "fusion.cu"]
+SOURCES = ["core.cu", "back_project_fwd.cu", "back_project_bwd.cu", "tsdf.cu", "level_glue.cu", "fusion.cu", "gt_crop.cu"]
 LIB = os.path.join(HERE, "libd3m.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true"]

@@ -625,6 +625,15 @@ extern "C" int d3m_tsdf_reset(d3m_tsdf* h, void* stream_) {
   return D3M_OK;
 }
 
+extern "C" int d3m_tsdf_rebase(d3m_tsdf* h, const float* origin3_host, float voxel_size, float trunc_margin,
+                               void* stream) {
+  D3M_REQUIRE(h && origin3_host && voxel_size > 0.f && trunc_margin > 0.f, D3M_ERR_ARG, "tsdf_rebase: bad arguments");
+  memcpy(h->origin, origin3_host, 12);
+  h->vs = voxel_size;
+  h->trunc = trunc_margin;
+  return d3m_tsdf_reset(h, stream);
+}
+
 static int upload_frames(d3m_tsdf* h, int F, int H, int W, const float* intr9_host, int intr_per_frame,
                          const float* pose16_host, const float* obs_host, float obs_scalar, int flags,
                          cudaStream_t stream, const Frame** d_out) {

@@ -273,6 +273,21 @@ class TSDFVolumeTorch:
     def reset(self):
         _lib.check(_lib.lib().d3m_tsdf_reset(self._h.ptr, self._stream), "d3m_tsdf_reset")
 
+    def rebase(self, origin, voxel_size=None, margin=None):
+        """Extension: re-use this object (and its device memory) for another volume of the same `voxel_dim` --
+        new origin / voxel size / margin, volumes reset.  Creating a handle costs ~10 ms of cudaMalloc / cudaFree."""
+        if voxel_size is not None:
+            m = self._sdf_trunc / self._voxel_size if margin is None else margin
+            self._voxel_size = float(voxel_size)
+            self._sdf_trunc = m * self._voxel_size
+        elif margin is not None:
+            self._sdf_trunc = margin * self._voxel_size
+        self._vol_origin = origin
+        org = np.ascontiguousarray(self._torch.as_tensor(origin).detach().float().cpu().numpy(), dtype=np.float32)
+        rc = _lib.lib().d3m_tsdf_rebase(self._h.ptr, _f32p(org), np.float32(self._voxel_size), np.float32(self._sdf_trunc),
+                                        self._stream)
+        _lib.check(rc, "d3m_tsdf_rebase")
+
     def integrate(self, depth_im, cam_intr, cam_pose, obs_weight):
         torch = self._torch
         cam_pose = cam_pose.float().cpu()
@@ -311,6 +326,12 @@ class TSDFVolumeTorch:
         _lib.check(_lib.lib().d3m_tsdf_download(self._h.ptr, _f32p(tsdf), _f32p(weight), None, self._stream),
                    "d3m_tsdf_download")
         return torch.from_numpy(tsdf), torch.from_numpy(weight)
+
+    def device_volumes(self):
+        """Extension: zero-copy CUDA tensors (tsdf, weight) over the handle's volumes (valid while `self` lives)."""
+        torch = self._torch
+        t, w, _ = self._h.volumes()
+        return torch.as_tensor(t, device="cuda"), torch.as_tensor(w, device="cuda")
 
     @property
     def sdf_trunc(self):

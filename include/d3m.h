@@ -154,6 +154,10 @@ int d3m_tsdf_create_slab(int dim_x_local, int dim_y, int dim_z, int x_begin, con
                          float voxel_size, float trunc_margin, int device, d3m_tsdf** out_handle);
 int d3m_tsdf_destroy(d3m_tsdf* h);
 int d3m_tsdf_reset(d3m_tsdf* h, void* stream);
+/* Re-use a handle for another volume of the same dimensions: new origin / voxel size / truncation, volumes reset
+ * (tsdf = 1, weight = colour = 0).  The dataloader transform (transforms_seq.py:355-357) builds three small
+ * volumes per sample; creating and destroying handles costs ~10 ms each (cudaMalloc / cudaMallocHost / cudaFree). */
+int d3m_tsdf_rebase(d3m_tsdf* h, const float* origin3_host, float voxel_size, float trunc_margin, void* stream);
 
 /* One frame from HOST memory -- the shape of TSDFVolume.integrate (:210-256): depth (H,W) float32
  * metres, optional colour (H,W) float32 already folded as b*65536+g*256+r (:223-227), intrinsics 3x3
@@ -177,6 +181,26 @@ int d3m_tsdf_download(d3m_tsdf* h, float* tsdf_host, float* weight_host, float* 
 /* voxels whose weight changed in the last integrate call is not tracked; this returns the number of
  * tile launches of the last call (diagnostics for bench.py's gpu_launches) */
 int d3m_tsdf_last_launches(d3m_tsdf* h);
+
+/* =============================================================================================
+ * SURVEY section 8 row f1, ground-truth side of the dataloader transform
+ * (deep3dmap/datasets/pipelines/transforms_seq.py:343-398, SeqRandomTransformSpace.transform).
+ * ========================================================================================== */
+
+/* :365-366  occ[i] = (tsdf[i] < hi) & (tsdf[i] > lo) & (weight[i] > min_weight)  on device arrays of n voxels
+ * (the reference uses lo = -0.999, hi = 0.999, min_weight = 1 on the volumes of TSDFVolumeTorch). */
+int d3m_tsdf_occupancy(const float* tsdf, const float* weight, int64_t n, float lo, float hi, float min_weight,
+                       uint8_t* occ, void* stream);
+
+/* :343-396  re-sample the full-scene TSDF `tsdf_full` (X,Y,Z) of level l on the transformed fragment grid:
+ *   c = ((transform[:3,:] @ [idx*step*voxel_size + vol_origin_partial, 1]) - old_origin) / voxel_size / step
+ *   g = 2*c/(dim-1) - 1 ;  nearest and trilinear 3-D grid_sample (align_corners=False, zero padding);
+ *   out = trilinear where |nearest| < 1 else nearest ;  out = 1 where any |g| >= 1.
+ * out is (nx,ny,nz) = voxel_dim / step, step = 2^l; the three small parameter arrays are HOST pointers
+ * (transform12 = the first three rows of the 4x4 matrix, row-major). */
+int d3m_gt_recrop(const float* tsdf_full, int X, int Y, int Z, int nx, int ny, int nz, int step, float voxel_size,
+                  const float* vol_origin_partial3_host, const float* transform12_host,
+                  const float* old_origin3_host, float* out, void* stream);
 
 /* =============================================================================================
  * the steps either side of back_project in the coarse-to-fine level loop

@@ -156,3 +156,60 @@ def neucon_modules():
     nn_ = load("deep3dmap/models/neucon_network.py", "deep3dmap.models.neucon_network")
     _neucon = (nn_, gf)
     return _neucon
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SURVEY §8 f1 (ground-truth side): the UNMODIFIED `SeqRandomTransformSpace` class of
+# datasets/pipelines/transforms_seq.py, loaded by path.  Its imports (PIL, transforms3d, the package __init__ chain,
+# the PIPELINES registry) are satisfied by stubs; `coordinates` is the reference's own function definition taken out
+# of neucon_utils.py's AST, `TSDFVolumeTorch` is the reference's own class (tsdf_module()).
+# ---------------------------------------------------------------------------------------------------------------
+_transforms = None
+
+
+def transforms_seq_module():
+    global _transforms
+    if _transforms is not None:
+        return _transforms
+    import ast
+
+    import torch
+
+    def stub(name, **attrs):
+        m = sys.modules.get(name)
+        if m is None:
+            m = types.ModuleType(name)
+            sys.modules[name] = m
+        m.__dict__.update(attrs)
+        return m
+
+    class _Registry:
+        def register_module(self, *a, **k):
+            return lambda cls: cls
+
+    for n in ("deep3dmap", "deep3dmap.core", "deep3dmap.core.utils", "deep3dmap.core.tsdf", "deep3dmap.datasets",
+              "deep3dmap.datasets.pipelines"):
+        m = stub(n)
+        if not hasattr(m, "__path__"):
+            m.__path__ = []
+    try:
+        import PIL  # noqa: F401
+    except Exception:
+        stub("PIL", Image=types.SimpleNamespace(), ImageOps=types.SimpleNamespace())
+    stub("transforms3d")
+    tree = ast.parse(open(os.path.join(REF_ROOT, "deep3dmap/core/utils/neucon_utils.py")).read())
+    body = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "coordinates"]
+    ns = {"torch": torch}
+    exec(compile(ast.Module(body=body, type_ignores=[]), "neucon_utils.py", "exec"), ns)
+    u = stub("deep3dmap.core.utils.neucon_utils")
+    u.coordinates = ns["coordinates"]
+    stub("deep3dmap.core.tsdf.tsdf_volume", TSDFVolumeTorch=tsdf_module().TSDFVolumeTorch)
+    stub("deep3dmap.datasets.pipelines.formating", to_tensor=torch.as_tensor)
+    stub("deep3dmap.datasets.builder", PIPELINES=_Registry())
+    spec = importlib.util.spec_from_file_location("deep3dmap.datasets.pipelines.transforms_seq",
+                                                  os.path.join(REF_ROOT, "deep3dmap/datasets/pipelines/transforms_seq.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod
+    spec.loader.exec_module(mod)
+    _transforms = mod
+    return mod
