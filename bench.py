@@ -256,6 +256,10 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    if args.legs == "datagen":
+        if rank == 0:
+            emit_json({"datagen": bench_datagen(torch, dev)})
+        return
     if args.legs == "glue":
         # quick pass over the f2 / f3 legs only (development and `ncu` target); one JSON line
         out = {"level_glue": {"fragment_x1": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 1),
@@ -433,8 +437,13 @@ def run_ours(args, rank, world, local_rank):
         tsdf = bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, with_cpu=(world == 1))
 
     # ---- SURVEY §8 rows f2 / f3 (rank 0 only): level glue around back_project, GRU-fusion volume movement ----
-    glue = fus = gtt = None
+    glue = fus = gtt = dgen = None
     if rank == 0:
+        try:
+            dgen = bench_datagen(torch, dev, with_cpu=(world == 1))
+        except Exception as err:
+            log("datagen leg failed:", repr(err))
+            dgen = {"error": repr(err)[:300]}
         try:
             glue = {"fragment_x1": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 1),
                     "fragments_x64": bench_level_glue(torch, dev, _lib, flush_buf, peak_gbs, 64, reps=3)}
@@ -531,6 +540,7 @@ def run_ours(args, rank, world, local_rank):
         "level_glue": glue,
         "gru_fusion": fus,
         "gt_transform": gtt,
+        "datagen": dgen,
     }
     emit_json(line)
     if world > 1:
@@ -1095,6 +1105,79 @@ def bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, quick=False, w
     return res
 
 
+def bench_datagen(torch, dev, with_cpu=True):
+    """the data-gen caller on the config-3 frames -- `save_tsdf_full` (tools/data_gen/scannet.py:49-128):
+    scene box from the frusta, 3 volumes, all 300 frames, tsdf_info.pkl + full_tsdf_layer{0,1,2}.npz on disk -- and
+    the reader of those files.  Baseline for the storage step = the reference's own call, `np.savez_compressed`
+    (single-threaded zlib), on the same arrays."""
+    import contextlib
+    import io
+    import shutil
+    import tempfile
+    import types
+    from deep3dmap_b200 import datagen, npzio
+    F = N_TSDF_FRAMES
+    K = synth.tsdf_intrinsics().astype(np.float64)
+    depth_list = {f: synth.tsdf_depth(f) for f in range(F)}
+    pose_list = {f: synth.tsdf_pose(f) for f in range(F)}
+    args = types.SimpleNamespace(num_layers=3, voxel_size=0.04, margin=3, window_size=9, min_angle=15, min_distance=0.1)
+    root = tempfile.mkdtemp(prefix="d3m_datagen_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    res = {"frames": F, "image": "480x640", "levels": 3}
+    try:
+        args.save_path = root
+        walls = []
+        for it in range(3):
+            shutil.rmtree(os.path.join(root, "scene"), ignore_errors=True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(io.StringIO()):
+                vols = datagen.save_tsdf_full(args, "scene", K, depth_list, pose_list, {})
+            walls.append(time.perf_counter() - t0)
+            if it < 2:
+                del vols
+        res["volume_dims"] = [[int(d) for d in v._vol_dim] for v in vols]
+        res["s_save_tsdf_full"] = min(walls)
+        res["scenes_frames_per_s"] = F / min(walls)
+        # split of the wall time
+        t0 = time.perf_counter()
+        bnds = datagen.scene_bounds(K, depth_list, pose_list)
+        res["s_scene_bounds_host"] = time.perf_counter() - t0
+        from deep3dmap_b200 import TSDFVolume
+        vs = [TSDFVolume(bnds, 0.04 * 2 ** l, margin=3) for l in range(3)]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res["integrate_launches"] = datagen._integrate_all(vs, K, depth_list, pose_list, {})
+        res["s_stage_and_integrate"] = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        datagen.write_scene_volumes(os.path.join(root, "scene"), vs)
+        res["s_download_and_write_npz"] = time.perf_counter() - t0
+        raw = sum(int(np.prod(v._vol_dim)) * 4 for v in vs)
+        res["volume_bytes"] = raw
+        res["npz_bytes"] = sum(os.path.getsize(os.path.join(root, "scene", "full_tsdf_layer%d.npz" % l)) for l in range(3))
+        t0 = time.perf_counter()
+        back = datagen.read_scene_volumes(root, "scene", 2)
+        res["s_read_scene_volumes"] = time.perf_counter() - t0
+        assert all(np.array_equal(b, v.get_volume()[0]) for b, v in zip(back, vs))
+        res["host_threads"] = min(32, os.cpu_count() or 1)
+        if with_cpu:
+            t0 = time.perf_counter()
+            for l, b in enumerate(back):
+                np.savez_compressed(os.path.join(root, "ref_layer%d" % l), b)
+            t_w = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for l in range(3):
+                full = np.load(os.path.join(root, "ref_layer%d.npz" % l), allow_pickle=True)
+                _ = full.f.arr_0
+            t_r = time.perf_counter() - t0
+            res["cpu_baseline"] = {"kind": "reference", "cores": 1, "unit": "s",
+                                   "s_write_np_savez_compressed": t_w, "s_read_np_load": t_r,
+                                   "sample": "the reference's own storage calls (scannet.py:115, datasets/scannet.py:"
+                                             "103-105) on the same three volumes; integration baseline: tsdf.cpu_baseline"}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+    return res
+
+
 class _StdoutGuard:
     """Exactly ONE JSON line may reach stdout: NCCL / torch occasionally print banners on fd 1, so fd 1 is pointed at
     stderr for the duration of the run and the JSON line is written to the saved descriptor."""
@@ -1134,7 +1217,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time the eager python path only")
-    ap.add_argument("--legs", default="all", choices=["all", "glue"], help="'glue': only the level-glue / GRU-fusion legs")
+    ap.add_argument("--legs", default="all", choices=["all", "glue", "datagen"], help="'glue': only the level-glue / GRU-fusion legs")
     ap.add_argument("--profile-step", default="", choices=["", "bp", "tsdf", "dense"],
                     help="profiler target: run only the hot-path steps (and the TSDF launches with 'tsdf'), print nothing")
     args = ap.parse_args()
