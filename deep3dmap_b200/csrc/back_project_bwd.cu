@@ -63,6 +63,7 @@ constexpr int kGhatSteps = 4;       // row groups in flight per warp of the pre-
 // Only used when the caller does not hand over the forward pass's `count`: valid views per voxel.
 template <int KIND>
 __global__ void __launch_bounds__(kSampleThreads) bp_bwd_count_kernel(const BwdParams p, float* __restrict__ cnt_out) {
+  pdl_enter();
   const int64_t n = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
   if (n >= p.N) return;
   float cx, cy, cz;
@@ -90,6 +91,7 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_count_kernel(const BwdP
 constexpr int kViewsPerThread = 3;  // independent atomics in flight per thread (the pass is latency-bound on them)
 template <int KIND, bool FILL>
 __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const BwdParams p) {
+  pdl_enter();
   const int v0 = blockIdx.y * kViewsPerThread;
   const int64_t n = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
   if (n >= p.N) return;
@@ -141,6 +143,7 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const Bwd
 //   ghat[n,c] = grad_out[n,c] / max(count[n],1)   (div backward of back_project.py:72), re-packed to 16-byte aligned
 //   rows of C floats (grad_out rows are (C+1) floats and cannot be vector-loaded).
 __global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdParams p) {
+  pdl_enter();
   __shared__ int red[kScanThreads / 32];
   __shared__ int s_cid, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -260,6 +263,7 @@ __global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdPar
 // This removes the only nondeterminism of the backward pass (the claim order of the fill atomics).
 constexpr int kOrderThreads = 256;
 __global__ void __launch_bounds__(kOrderThreads) bp_bwd_order_kernel(const BwdParams p) {
+  pdl_enter();
   const int total = __ldg(p.bin_start + p.Mb);
   for (int i = blockIdx.x * kOrderThreads + threadIdx.x; i < total; i += gridDim.x * kOrderThreads) {
     const int4 e = __ldg(p.entries + i);
@@ -335,6 +339,7 @@ template <int G, int R>
 __global__ void __launch_bounds__(kGatherWarps * 32, (R == 1 ? 4 : 3)) bp_bwd_gather_tile_kernel(const BwdParams p, const int TX,
                                                                                const int TY, const int tiles_x,
                                                                                const int tiles_y) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char gsm[];
   __shared__ int s_big[kMaxBig];
   __shared__ int s_nbig;
@@ -496,6 +501,7 @@ __global__ void __launch_bounds__(kGatherWarps * 32, (R == 1 ? 4 : 3)) bp_bwd_ga
 
 // any C: one warp per texel, lanes stride over channels
 __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_generic_kernel(const BwdParams p) {
+  pdl_enter();
   const int lane = threadIdx.x & 31;
   const int C = p.C;
   const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -618,16 +624,19 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  D3M_CUDA_CHECK(cudaMemsetAsync(zero_from, 0, zero_bytes, stream));
+  {
+    const int zrc = zero_async(zero_from, zero_bytes, stream);
+    if (zrc != D3M_OK) return zrc;
+  }
   const unsigned vox_ctas = (unsigned)((p.N + kSampleThreads - 1) / kSampleThreads);
   if (cnt_ws) {  // no forward count handed over: recompute it
     LaunchScope ls("bp_bwd_count", stream);
-    bp_bwd_count_kernel<KIND><<<vox_ctas, kSampleThreads, 0, stream>>>(p, cnt_ws);
+    launch_k(bp_bwd_count_kernel<KIND>, dim3(vox_ctas), dim3(kSampleThreads), 0, stream, p, cnt_ws);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   if (!have_hist) {
     LaunchScope ls("bp_bwd_hist", stream);
-    bp_bwd_sample_kernel<KIND, false><<<dim3(vox_ctas, (p.V + kViewsPerThread - 1) / kViewsPerThread), kSampleThreads, 0, stream>>>(p);
+    launch_k(bp_bwd_sample_kernel<KIND, false>, dim3(vox_ctas, (p.V + kViewsPerThread - 1) / kViewsPerThread), dim3(kSampleThreads), 0, stream, p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
@@ -635,12 +644,12 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
     const int64_t rows_per_cta = (int64_t)(kScanThreads / 32) * kGhatSteps * rows_per_step;
     const int64_t ghat_blocks = (p.N + rows_per_cta - 1) / rows_per_cta;
     LaunchScope ls("bp_bwd_scan_ghat", stream);
-    bp_scan_ghat_kernel<<<(unsigned)(p.nchunks + ghat_blocks), kScanThreads, 0, stream>>>(p);
+    launch_k(bp_scan_ghat_kernel, dim3((unsigned)(p.nchunks + ghat_blocks)), dim3(kScanThreads), 0, stream, p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
     LaunchScope ls("bp_bwd_fill", stream);
-    bp_bwd_sample_kernel<KIND, true><<<dim3(vox_ctas, (p.V + kViewsPerThread - 1) / kViewsPerThread), kSampleThreads, 0, stream>>>(p);
+    launch_k(bp_bwd_sample_kernel<KIND, true>, dim3(vox_ctas, (p.V + kViewsPerThread - 1) / kViewsPerThread), dim3(kSampleThreads), 0, stream, p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   {
@@ -648,7 +657,7 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
     if (ctas > (int64_t)sms * 16) ctas = (int64_t)sms * 16;
     if (ctas < 1) ctas = 1;
     LaunchScope ls("bp_bwd_order", stream);
-    bp_bwd_order_kernel<<<(unsigned)ctas, kOrderThreads, 0, stream>>>(p);
+    launch_k(bp_bwd_order_kernel, dim3((unsigned)ctas), dim3(kOrderThreads), 0, stream, p);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
   gather_kernel_t k = pick_gather_kernel(p.C);
@@ -662,7 +671,7 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
     smem += (size_t)kGatherWarps * 4 * p.C * 4;  // scratch of the cooperative big-cell pass
     D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     LaunchScope ls("bp_bwd_gather", stream);
-    k<<<(unsigned)tiles, kGatherWarps * 32, smem, stream>>>(p, TX, TY, tiles_x, tiles_y);
+    launch_k(k, dim3((unsigned)tiles), dim3(kGatherWarps * 32), smem, stream, p, TX, TY, tiles_x, tiles_y);
     D3M_CUDA_CHECK(cudaGetLastError());
   } else {
     D3M_REQUIRE(p.C <= 256, D3M_ERR_ARG, "back_project backward: C=%d unsupported (C%%4!=0 needs C<=256)", p.C);
@@ -670,7 +679,7 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
     if (ctas > (int64_t)sms * 16) ctas = (int64_t)sms * 16;
     if (ctas < 1) ctas = 1;
     LaunchScope ls("bp_bwd_gather", stream);
-    bp_bwd_gather_generic_kernel<<<(unsigned)ctas, kGatherWarps * 32, 0, stream>>>(p);
+    launch_k(bp_bwd_gather_generic_kernel, dim3((unsigned)ctas), dim3(kGatherWarps * 32), 0, stream, p);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
   return D3M_OK;

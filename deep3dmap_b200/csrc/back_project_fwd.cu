@@ -43,6 +43,7 @@ struct FwdParams {
   int* cell_hist;         // optional histogram of valid samples per (bilinear cell, voxel bucket) bin, consumed by backward
   int nb_log2;            // BinCfg of this call
   int tv;
+  int stage_kr;           // 1: per-warp shared-memory staging of the projection rows (stage_krcam)
   int vchunk;
   int64_t num_tiles;
   int per_warp_bytes;
@@ -62,16 +63,38 @@ __device__ __forceinline__ void bulk_store_tile(float* gdst, const float* ssrc, 
   __syncwarp();
 }
 
+// The per-view projection rows are read by every voxel of a tile.  Loading them inside the view loop makes each warp pay
+// one dependent L2 (first touch: DRAM) round trip per view -- 9 in a row at fragment size, where one warp's latency IS the
+// kernel's duration.  Instead the warp fetches the whole chunk (3 x 128 bit per view) of its first voxel's fragment with
+// one batch of independent loads and broadcasts from shared memory; voxels of another fragment fall back to global loads.
+__device__ __forceinline__ void stage_krcam(const FwdParams& p, int bt, int v0, int v1, int lane, float4* kr_s) {
+  if (bt >= 0) {
+    const float4* KR4 = reinterpret_cast<const float4*>(p.KR);
+    for (int i = lane; i < 3 * (v1 - v0); i += 32) {
+      const int v = v0 + i / 3, r = i - 3 * (i / 3);
+      kr_s[i] = __ldg(KR4 + ((int64_t)v * p.B + bt) * 4 + r);
+    }
+  }
+  __syncwarp();
+}
+
 // phase 1 for one chunk of views; returns the number of records pushed by this lane
+// kr_s / bt: the chunk's projection rows of fragment `bt`, staged in shared memory by stage_krcam (NULL: not staged)
 template <int KIND>
 __device__ __forceinline__ int push_records(const FwdParams& p, int b, int64_t n, float gx, float gy, float gz, int v0,
-                                            int v1, int lane, int* rec_off, float* rec_fx, float* rec_fy, float& zsum) {
+                                            int v1, int lane, int* rec_off, float* rec_fx, float* rec_fy, float& zsum,
+                                            const float4* kr_s = nullptr, int bt = -1) {
   int ccnt = 0;
   if (b >= 0) {
     const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
+    const bool staged = kr_s != nullptr && b == bt;
     for (int v = v0; v < v1; ++v) {
       float4 r0, r1, r2;
-      load_krcam(p.KR, v, p.B, b, r0, r1, r2);
+      if (staged) {
+        r0 = kr_s[3 * (v - v0)]; r1 = kr_s[3 * (v - v0) + 1]; r2 = kr_s[3 * (v - v0) + 2];
+      } else {
+        load_krcam(p.KR, v, p.B, b, r0, r1, r2);
+      }
       const Sample s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
       if (s.valid) {
         int off = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
@@ -96,8 +119,9 @@ __device__ __forceinline__ float corner_chain(float t00, float t01, float t10, f
   return __fmaf_rn(t11, se, __fmaf_rn(t10, sw, __fmaf_rn(t01, ne, __fmul_rn(t00, nw))));
 }
 
-template <int KIND, int G, int R>
+template <int KIND, int G, int R, int KU>
 __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams p) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   constexpr int NG = 32 / G;  // lane groups per warp
@@ -108,6 +132,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
   int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
   float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
   float* rec_fy = rec_fx + p.vchunk * 32;
+  float4* kr_s = p.stage_kr ? reinterpret_cast<float4*>(rec_fy + p.vchunk * 32) : nullptr;
   const float4* __restrict__ feats4 = reinterpret_cast<const float4*>(p.feats);
   if (blockIdx.x == 0 && threadIdx.x == 0) *p.counter = 0u;
 
@@ -131,7 +156,9 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
     for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
       const int v1 = min(p.V, v0 + p.vchunk);
       const bool first = (v0 == 0), last = (v1 == p.V);
-      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      const int bt = __shfl_sync(kFull, b, 0);
+      if (kr_s) stage_krcam(p, bt, v0, v1, lane, kr_s);
+      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum, kr_s, bt);
       cnt += ccnt;
       __syncwarp();
       for (int r = 0; r * NG < p.tv; ++r) {
@@ -151,7 +178,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
             acc[i] = make_float4(q[0], q[1], q[2], q[3]);
           }
         }
-#pragma unroll 2
+#pragma unroll KU
         for (int k = 0; k < kmax; ++k) {
           const bool on = k < cj;
           const int jj = on ? j : 0;
@@ -222,6 +249,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
 constexpr int kGenericMaxR = 8;
 template <int KIND>
 __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const FwdParams p) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int C = p.C, C1 = C + 1;
@@ -361,6 +389,7 @@ __device__ __forceinline__ double warp_sum(double v) {
 }
 
 __global__ void __launch_bounds__(kStatsThreads) bp_stats_kernel(const StatsParams p) {
+  pdl_enter();
   __shared__ double red[3][kStatsThreads / 32];
   __shared__ int s_bmin, s_bmax;
   __shared__ bool s_last;
@@ -446,6 +475,7 @@ __global__ void __launch_bounds__(kStatsThreads) bp_stats_kernel(const StatsPara
 
 // voxel-range sharding: stats from the all-reduced sums of every shard
 __global__ void bp_stats_from_sums_kernel(const double* __restrict__ sums, float* __restrict__ stats, int B) {
+  pdl_enter();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   float mean, sd;
@@ -457,6 +487,7 @@ __global__ void bp_stats_from_sums_kernel(const double* __restrict__ sums, float
 __global__ void __launch_bounds__(256) bp_normalise_kernel(const float* __restrict__ zbar, const int* __restrict__ bidx,
                                                            const float* __restrict__ stats, float* __restrict__ out,
                                                            int64_t N, int C1) {
+  pdl_enter();
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int b = bidx[n];
@@ -501,17 +532,27 @@ typedef void (*fwd_kernel_t)(const FwdParams);
 
 // (G lanes x R float4 per lane) = C/4 channel quads per voxel.  The table lists every instantiated shape; for a given
 // C the FIRST matching row is the default, D3M_FWD_GR="C:G:R[,C:G:R...]" (tuning aid) selects another one.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 template <int KIND>
-static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
-  struct Row { int g, r; fwd_kernel_t k; };
-#define D3M_FWD_ROW(g, r) {g, r, bp_fwd_kernel<KIND, g, r>}
+static fwd_kernel_t pick_fwd_kernel(int C, int ku_want, int& G, int& R) {
+  struct Row { int g, r, ku; fwd_kernel_t k; };
+#define D3M_FWD_ROW(g, r) {g, r, 2, bp_fwd_kernel<KIND, g, r, 2>}
+#define D3M_FWD_ROW4(g, r) {g, r, 4, bp_fwd_kernel<KIND, g, r, 4>}
   static const Row rows[] = {
       D3M_FWD_ROW(6, 1),  D3M_FWD_ROW(3, 2),  D3M_FWD_ROW(2, 3),                    // C = 24  (level 2)
       D3M_FWD_ROW(10, 1), D3M_FWD_ROW(5, 2),  D3M_FWD_ROW(2, 5),                    // C = 40  (level 1)
       D3M_FWD_ROW(10, 2), D3M_FWD_ROW(5, 4),  D3M_FWD_ROW(4, 5),                    // C = 80  (level 0)
       D3M_FWD_ROW(4, 1),  D3M_FWD_ROW(8, 1),  D3M_FWD_ROW(16, 1), D3M_FWD_ROW(8, 3), D3M_FWD_ROW(16, 2),
-      D3M_FWD_ROW(2, 1),  D3M_FWD_ROW(3, 1),  D3M_FWD_ROW(5, 1)};
+      D3M_FWD_ROW(2, 1),  D3M_FWD_ROW(3, 1),  D3M_FWD_ROW(5, 1),
+      // deeper software pipelining of the sample loop (4 samples' corner loads in flight per lane group) for the
+      // single-wave, latency-bound launches of fragment-sized levels
+      D3M_FWD_ROW4(6, 1), D3M_FWD_ROW4(10, 1), D3M_FWD_ROW4(10, 2)};
 #undef D3M_FWD_ROW
+#undef D3M_FWD_ROW4
   G = 0; R = 0;
   if (C % 4 != 0) return nullptr;
   const int q = C / 4;
@@ -525,36 +566,50 @@ static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
     }
   }
   const Row* pick = nullptr;
-  for (const Row& row : rows) {
-    if (row.g * row.r != q) continue;
+  for (const Row& row : rows) {  // shape first (the first ku = 2 row of that shape is the default) ...
+    if (row.g * row.r != q || row.ku != 2) continue;
     if (!pick) pick = &row;
     if (row.g == want_g && row.r == want_r) { pick = &row; break; }
   }
   if (!pick) return nullptr;
+  for (const Row& row : rows)  // ... then the requested pipelining depth of that shape, when it is instantiated
+    if (row.g == pick->g && row.r == pick->r && row.ku == ku_want) { pick = &row; break; }
   G = pick->g; R = pick->r;
   return pick->k;
 }
 
+// Launch shape.  Large N: 32-voxel warp tiles, grid capped at 32 CTAs per SM (grid-stride).  Small N (the launch is a single
+// wave): the kernel's duration is ONE warp's latency chain -- views x projection, then tile/NG rounds of count[n] dependent
+// gather steps -- so the tile shrinks (down to D3M_FWD_TVMIN voxels, a multiple of 4 to keep the bulk store 16-byte aligned)
+// until the GPU holds D3M_FWD_WARPS_PER_SM warps per SM, and the sample loop is pipelined 4 deep (D3M_FWD_KU).
 template <int KIND>
 static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   FwdParams p = p0;
-  int G, R;
-  fwd_kernel_t k = pick_fwd_kernel<KIND>(p.C, G, R);
-  if (!k) {
-    D3M_REQUIRE(p.C <= 32 * kGenericMaxR, D3M_ERR_ARG, "back_project: C=%d unsupported (C%%4!=0 needs C<=%d)", p.C,
-                32 * kGenericMaxR);
-    k = bp_fwd_generic_kernel<KIND>;
-  }
+  static const int tv_min = env_int("D3M_FWD_TVMIN", 8);
+  static const int warps_per_sm = env_int("D3M_FWD_WARPS_PER_SM", 16);
+  static const int ku_small = env_int("D3M_FWD_KU", 2);
+  static const int stage_kr = env_int("D3M_FWD_STAGE_KR", 1);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   // voxels per warp tile: 32 for large N; shrink for small N so every SM still gets several warps
   int tv = 32;
-  while (tv > 8 && (p.N + tv - 1) / tv < (int64_t)sms * 16) tv >>= 1;
+  const int tv_floor = tv_min >= 4 && tv_min <= 32 && (tv_min & (tv_min - 1)) == 0 ? tv_min : 8;
+  while (tv > tv_floor && (p.N + tv - 1) / tv < (int64_t)sms * warps_per_sm) tv >>= 1;
+  const bool small = tv < 32;
+  int G, R;
+  fwd_kernel_t k = pick_fwd_kernel<KIND>(p.C, small ? ku_small : 2, G, R);
+  if (!k) {
+    D3M_REQUIRE(p.C <= 32 * kGenericMaxR, D3M_ERR_ARG, "back_project: C=%d unsupported (C%%4!=0 needs C<=%d)", p.C,
+                32 * kGenericMaxR);
+    k = bp_fwd_generic_kernel<KIND>;
+  }
   p.tv = tv;
+  p.stage_kr = stage_kr ? 1 : 0;
   p.vchunk = p.V < kMaxViewChunk ? p.V : kMaxViewChunk;
   p.num_tiles = (p.N + tv - 1) / tv;
-  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)3 * p.vchunk * 32 * 4, 16);
+  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)3 * p.vchunk * 32 * 4 +
+                                       (size_t)p.vchunk * 48, 16);
   const size_t smem = (size_t)p.per_warp_bytes * kFwdWarps;
   D3M_REQUIRE(smem <= 200 * 1024, D3M_ERR_ARG, "back_project: C=%d needs %zu B shared memory per CTA", p.C, smem);
   D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -564,7 +619,7 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   if (ctas < 1) ctas = 1;
   {
     LaunchScope ls("bp_fwd", stream);
-    k<<<(unsigned)ctas, kFwdWarps * 32, smem, stream>>>(p);
+    D3M_CUDA_CHECK(launch_k(k, dim3((unsigned)ctas), dim3(kFwdWarps * 32), smem, stream, p));
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
@@ -608,7 +663,7 @@ static int fwd_check(const void* coords, int coords_kind, int64_t N, const float
 
 static int fwd_normalise(int64_t N, int C, const FwdWs& w, unsigned char* ws, float* out, cudaStream_t stream) {
   LaunchScope ls("bp_fwd_normalise", stream);
-  bp_normalise_kernel<<<(unsigned)((N + 255) / 256), 256, 0, stream>>>(
+  launch_k(bp_normalise_kernel, dim3((unsigned)((N + 255) / 256)), dim3(256), 0, stream, 
       reinterpret_cast<const float*>(ws + w.zbar), reinterpret_cast<const int*>(ws + w.bidx),
       reinterpret_cast<const float*>(ws + w.stats), out, N, C + 1);
   D3M_CUDA_CHECK(cudaGetLastError());
@@ -625,7 +680,8 @@ static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float*
   if (rc != D3M_OK) return rc;
   if (cell_hist) {
     D3M_REQUIRE(aligned16(cell_hist), D3M_ERR_ALIGN, "back_project: cell_hist must be 16-byte aligned");
-    D3M_CUDA_CHECK(cudaMemsetAsync(cell_hist, 0, sizeof(int) * d3m_back_project_cell_hist_elems(N, B, V, H, W), stream));
+    rc = zero_async(cell_hist, sizeof(int) * d3m_back_project_cell_hist_elems(N, B, V, H, W), stream);
+    if (rc != D3M_OK) return rc;
   }
   if (N == 0) {
     if (depth_sums) D3M_CUDA_CHECK(cudaMemsetAsync(depth_sums, 0, sizeof(double) * 3 * (size_t)B, stream));
@@ -657,7 +713,7 @@ static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float*
   sp.finalize = depth_sums ? 0 : 1;
   {
     LaunchScope ls("bp_fwd_stats", stream);
-    bp_stats_kernel<<<w.nchunks, kStatsThreads, 0, stream>>>(sp);
+    launch_k(bp_stats_kernel, dim3(w.nchunks), dim3(kStatsThreads), 0, stream, sp);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   if (depth_sums) return D3M_OK;
@@ -695,7 +751,7 @@ extern "C" int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   {
     LaunchScope ls("bp_fwd_stats_from_sums", stream);
-    bp_stats_from_sums_kernel<<<(B + 127) / 128, 128, 0, stream>>>(depth_sums, reinterpret_cast<float*>(ws + w.stats), B);
+    launch_k(bp_stats_from_sums_kernel, dim3((B + 127) / 128), dim3(128), 0, stream, depth_sums, reinterpret_cast<float*>(ws + w.stats), B);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   return fwd_normalise(N, C, w, ws, out, stream);

@@ -26,6 +26,14 @@ int cuda_fail(cudaError_t e, const char* what) {
   return D3M_ERR_CUDA + (int)e;
 }
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("D3M_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 static std::atomic<long long> g_launches{0};
 static std::atomic<bool> g_profiling{false};
 static std::mutex g_prof_mu;
@@ -52,9 +60,36 @@ LaunchScope::~LaunchScope() {
   }
 }
 
+// Clears `bytes` (multiple of 4, 16-byte aligned start) with a kernel instead of a memset node, so that the clear takes
+// part in the programmatic-dependent-launch chain of d3m_common.cuh (a memset between two kernels serialises them fully).
+__global__ void __launch_bounds__(256) zero_words_kernel(uint32_t* __restrict__ p, int64_t n_words) {
+  pdl_enter();
+  const int64_t nv = n_words >> 2;
+  uint4* v = reinterpret_cast<uint4*>(p);
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < nv; i += (int64_t)gridDim.x * 256)
+    v[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n_words & 3)) p[(nv << 2) + threadIdx.x] = 0u;
+}
+
+int zero_async(void* p, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0) return D3M_OK;
+  if (!pdl_enabled() || (bytes & 3) || !aligned16(p)) {
+    D3M_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream));
+    return D3M_OK;
+  }
+  const int64_t words = (int64_t)(bytes >> 2);
+  int64_t ctas = ((words >> 2) + 255) / 256;
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  if (ctas < 1) ctas = 1;
+  LaunchScope ls("zero_words", stream);
+  D3M_CUDA_CHECK(launch_k(zero_words_kernel, dim3((unsigned)ctas), dim3(256), 0, stream, static_cast<uint32_t*>(p), words));
+  return D3M_OK;
+}
+
 // (n_maps, A, Bn) -> (n_maps, Bn, A) through a padded 32x32 shared-memory tile: both sides coalesced.
 __global__ void __launch_bounds__(256) transpose_maps_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                              int A, int Bn) {
+  pdl_enter();
   __shared__ float tile[32][33];
   const int64_t map = blockIdx.z;
   const float* s = src + map * (int64_t)A * Bn;
@@ -82,7 +117,7 @@ static int transpose_maps(const float* src, float* dst, int64_t n_maps, int A, i
     const unsigned nz = (unsigned)((n_maps - m0) < 65535 ? (n_maps - m0) : 65535);
     dim3 grid((Bn + 31) / 32, (A + 31) / 32, nz);
     LaunchScope ls("relayout_transpose", stream);
-    transpose_maps_kernel<<<grid, 256, 0, stream>>>(src + m0 * (int64_t)A * Bn, dst + m0 * (int64_t)A * Bn, A, Bn);
+    launch_k(transpose_maps_kernel, dim3(grid), dim3(256), 0, stream, src + m0 * (int64_t)A * Bn, dst + m0 * (int64_t)A * Bn, A, Bn);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
   return D3M_OK;

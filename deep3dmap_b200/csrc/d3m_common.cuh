@@ -38,6 +38,43 @@ struct LaunchScope {
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ------------------------------------------------------------------------------------------------
+// Programmatic dependent launch (griddepcontrol, sm_90+).  The fragment-sized step is a chain of 5-45 us kernels, so
+// the launch ramp of kernel K+1 (CTA dispatch, parameter and instruction fetch) is a visible share of the step.  Every
+// kernel of the chain starts with pdl_enter(): wait until the kernel before it has completed and its writes are
+// visible, THEN allow the next kernel of the stream to be dispatched.  A successor launched through launch_k() therefore
+// becomes resident while this kernel is still running (its CTAs block in griddepcontrol.wait and fill the SMs as ours
+// drain) instead of after our last CTA has retired.  Look-ahead is one kernel deep by construction, and a successor is
+// only dispatched once every CTA of its predecessor has started, so waiting CTAs can never starve running ones.
+// Without the launch attribute (plain <<< >>>, D3M_PDL=0, or a memset / torch op in between) both instructions are no-ops
+// and the stream serialises as usual.  Works in eager streams and inside CUDA-graph capture (programmatic edges).
+// ------------------------------------------------------------------------------------------------
+bool pdl_enabled();  // core.cu: env D3M_PDL != "0"
+
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                   Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// zero-fill on the stream: a PDL-chained kernel (core.cu) when it can be, cudaMemsetAsync otherwise
+int zero_async(void* p, size_t bytes, cudaStream_t stream);
+
+// ------------------------------------------------------------------------------------------------
 // Backward binning.  A bin = (bilinear cell (v,b,y0,x0), voxel bucket n & (nb-1)): bins are ordered cell-major,
 // bucket-minor, so a cell's entries stay contiguous; inside a bin the entries are ranked by voxel index.  The resulting
 // accumulation order per cell -- (low bits of the voxel index, voxel index) -- is a pure function of the inputs, which

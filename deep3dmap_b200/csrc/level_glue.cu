@@ -15,6 +15,7 @@ static inline unsigned blocks_for(int64_t n, int per_block) { return (unsigned)(
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) grid_coords_kernel(int gy, int gz, int64_t n_per, int interval, int B,
                                                           float4* __restrict__ coords, float* __restrict__ grid3) {
+  pdl_enter();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_per * (coords ? B : 1)) return;
   const int b = (int)(t / n_per);
@@ -47,6 +48,7 @@ __device__ __forceinline__ void child_offsets(int i, int& dx, int& dy, int& dz) 
 template <int KIND>
 __global__ void __launch_bounds__(256) upsample_coords_kernel(const void* __restrict__ pre, int64_t total, int num,
                                                               int interval, void* __restrict__ up) {
+  pdl_enter();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int64_t n = t / num;
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(256) upsample_coords_kernel(const void* __rest
 template <typename VecT, typename IdxT>
 __global__ void __launch_bounds__(256) upsample_feat_kernel(const VecT* __restrict__ pre, IdxT total_vec, IdxT vec_per_row,
                                                             int num, VecT* __restrict__ up) {
+  pdl_enter();
   const IdxT t = (IdxT)blockIdx.x * (IdxT)blockDim.x + threadIdx.x;
   if (t >= total_vec) return;
   const IdxT n = t / vec_per_row;
@@ -100,10 +103,10 @@ static void launch_upsample_feat(const float* pre, int64_t N, int C, int num, fl
   const int per = (int)(sizeof(VecT) / 4);
   const int64_t vpr = C / per, total = N * vpr;
   if (total < (1ll << 32)) {
-    upsample_feat_kernel<VecT, uint32_t><<<blocks_for(total, 256), 256, 0, stream>>>(
+    launch_k(upsample_feat_kernel<VecT, uint32_t>, dim3(blocks_for(total, 256)), dim3(256), 0, stream, 
         reinterpret_cast<const VecT*>(pre), (uint32_t)total, (uint32_t)vpr, num, reinterpret_cast<VecT*>(up));
   } else {
-    upsample_feat_kernel<VecT, uint64_t><<<blocks_for(total, 256), 256, 0, stream>>>(
+    launch_k(upsample_feat_kernel<VecT, uint64_t>, dim3(blocks_for(total, 256)), dim3(256), 0, stream, 
         reinterpret_cast<const VecT*>(pre), (uint64_t)total, (uint64_t)vpr, num, reinterpret_cast<VecT*>(up));
   }
 }
@@ -118,6 +121,7 @@ __global__ void __launch_bounds__(256) aligned_camera_kernel(const void* __restr
                                                              const float* __restrict__ origin, int B, float vs,
                                                              const float* __restrict__ w2ac,
                                                              float4* __restrict__ out) {
+  pdl_enter();
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   float x, y, z, bf;
@@ -151,6 +155,7 @@ __global__ void __launch_bounds__(256) gather_targets_kernel(const void* __restr
                                                              const uint8_t* __restrict__ occ_vol, int B, int X, int Y,
                                                              int Z, float* __restrict__ tsdf_out,
                                                              uint8_t* __restrict__ occ_out, int* __restrict__ bad) {
+  pdl_enter();
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   long long b, x, y, z;
@@ -198,6 +203,7 @@ __global__ void __launch_bounds__(256) occupancy_flags_kernel(const float* __res
                                                               const float* __restrict__ count, float min_count,
                                                               const uint8_t* __restrict__ mask, float thr, int64_t N,
                                                               uint8_t* __restrict__ flags) {
+  pdl_enter();
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   bool f = __ldg(occ + n * occ_stride) > thr;
@@ -243,6 +249,7 @@ __device__ __forceinline__ unsigned load_flags16(const uint8_t* __restrict__ fla
 __global__ void __launch_bounds__(CMP_THREADS) compact_count_kernel(const uint8_t* __restrict__ flags, int64_t N,
                                                                     bool aligned, bool invert,
                                                                     int64_t* __restrict__ chunk_count) {
+  pdl_enter();
   const int64_t base = (int64_t)blockIdx.x * CMP_CHUNK + (int64_t)threadIdx.x * CMP_ITEMS;
   int c = base < N ? __popc(load_flags16(flags, base, N, aligned, invert)) : 0;
   __shared__ int warp_sum[CMP_THREADS / 32];
@@ -260,6 +267,7 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_count_kernel(const uint8_
 
 __global__ void __launch_bounds__(1024) compact_scan_kernel(int64_t* __restrict__ chunk_count, int64_t n_chunks,
                                                             int64_t* __restrict__ total_out) {
+  pdl_enter();
   __shared__ int64_t warp_tot[32];
   __shared__ int64_t tile_total;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -300,6 +308,7 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_write_kernel(const uint8_
                                                                     const int64_t* __restrict__ chunk_offset,
                                                                     const int64_t* __restrict__ values,
                                                                     OutT* __restrict__ out) {
+  pdl_enter();
   const int64_t base = (int64_t)blockIdx.x * CMP_CHUNK + (int64_t)threadIdx.x * CMP_ITEMS;
   const unsigned m = base < N ? load_flags16(flags, base, N, aligned, invert) : 0u;
   const int c = __popc(m);
@@ -331,6 +340,7 @@ __global__ void __launch_bounds__(CMP_THREADS) compact_write_kernel(const uint8_
 __global__ void __launch_bounds__(256) drop_ranks_kernel(const int64_t* __restrict__ choice, int64_t n_choice,
                                                          int64_t n_keep, uint8_t* __restrict__ keep,
                                                          int* __restrict__ bad) {
+  pdl_enter();
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n_choice) return;
   const int64_t r = __ldg(choice + j);
@@ -349,6 +359,7 @@ template <typename VecT>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const VecT* __restrict__ src, int vec_per_row,
                                                           const int64_t* __restrict__ ind, int64_t total,
                                                           VecT* __restrict__ dst) {
+  pdl_enter();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int64_t m = t / vec_per_row;
@@ -366,6 +377,7 @@ struct ConcatSrc {
 // Generic path (any widths / alignment): one thread per output float.
 __global__ void __launch_bounds__(256) gather_concat_kernel(ConcatSrc s, const int64_t* __restrict__ ind,
                                                             int64_t total, float* __restrict__ dst) {
+  pdl_enter();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   const int wtot = s.begin[s.n];
@@ -388,6 +400,7 @@ constexpr int GC_UNROLL = 4;
 __global__ void __launch_bounds__(256) gather_concat_pair_kernel(ConcatSrc s, const int64_t* __restrict__ ind,
                                                                  uint32_t total_units, uint32_t units_per_row,
                                                                  float2* __restrict__ dst) {
+  pdl_enter();
   const uint32_t t0 = (blockIdx.x * (uint32_t)blockDim.x * GC_UNROLL) + threadIdx.x;
   float2 v[GC_UNROLL];
 #pragma unroll
@@ -433,6 +446,7 @@ __global__ void __launch_bounds__(256) gather_concat_pair_kernel(ConcatSrc s, co
 constexpr int GC_ROWS = 32;
 __global__ void __launch_bounds__(256) gather_concat_tile_kernel(ConcatSrc s, const int64_t* __restrict__ ind, int64_t M,
                                                                  float* __restrict__ dst) {
+  pdl_enter();
   extern __shared__ __align__(16) float gc_tile[];
   __shared__ int64_t rows[GC_ROWS];
   const int wtot = s.begin[s.n];
@@ -477,6 +491,7 @@ __global__ void __launch_bounds__(256) gather_concat_tile_kernel(ConcatSrc s, co
 template <int KIND>
 __global__ void __launch_bounds__(256) batch_counts_kernel(const void* __restrict__ coords, int64_t N, int B,
                                                            unsigned long long* __restrict__ counts) {
+  pdl_enter();
   const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int b = -1;
   if (n < N) {
@@ -527,7 +542,7 @@ extern "C" int d3m_grid_coords(int nx, int ny, int nz, int interval, int B, floa
   const int64_t total = n_per * (coords ? B : 1);
   if (total == 0) return D3M_OK;
   LaunchScope ls("grid_coords", stream);
-  grid_coords_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(gy, gz, n_per, interval, B,
+  launch_k(grid_coords_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, stream, gy, gz, n_per, interval, B,
                                                                 reinterpret_cast<float4*>(coords), grid3);
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
@@ -546,7 +561,7 @@ extern "C" int d3m_upsample(const void* pre_coords, int coords_kind, const float
     D3M_REQUIRE(aligned16(up_coords), D3M_ERR_ALIGN, "d3m_upsample: up_coords must be 16-byte aligned");
     const int64_t total = N * num;
     LaunchScope ls("upsample_coords", stream);
-    D3M_DISPATCH_KIND(coords_kind, (upsample_coords_kernel<K><<<blocks_for(total, 256), 256, 0, stream>>>(
+    D3M_DISPATCH_KIND(coords_kind, (launch_k(upsample_coords_kernel<K>, dim3(blocks_for(total, 256)), dim3(256), 0, stream, 
                                        pre_coords, total, num, interval, up_coords)));
     D3M_CUDA_CHECK(cudaGetLastError());
   }
@@ -580,7 +595,7 @@ extern "C" int d3m_aligned_camera_coords(const void* coords, int coords_kind, in
               "d3m_aligned_camera_coords: r_coords / matrices must be 16-byte aligned");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LaunchScope ls("aligned_camera_coords", stream);
-  D3M_DISPATCH_KIND(coords_kind, (aligned_camera_kernel<K><<<blocks_for(N, 256), 256, 0, stream>>>(
+  D3M_DISPATCH_KIND(coords_kind, (launch_k(aligned_camera_kernel<K>, dim3(blocks_for(N, 256)), dim3(256), 0, stream, 
                                      coords, N, origin, B, voxel_size, world_to_aligned_camera,
                                      reinterpret_cast<float4*>(r_coords))));
   D3M_CUDA_CHECK(cudaGetLastError());
@@ -601,7 +616,7 @@ extern "C" int d3m_gather_targets(const void* coords, int coords_kind, int64_t N
   int rc = check_kind(coords_kind, coords, "d3m_gather_targets");
   if (rc) return rc;
   LaunchScope ls("gather_targets", stream);
-  D3M_DISPATCH_KIND(coords_kind, (gather_targets_kernel<K><<<blocks_for(N, 256), 256, 0, stream>>>(
+  D3M_DISPATCH_KIND(coords_kind, (launch_k(gather_targets_kernel<K>, dim3(blocks_for(N, 256)), dim3(256), 0, stream, 
                                      coords, N, divisor, tsdf_vol, occ_vol, B, X, Y, Z, tsdf_out, occ_out, bad_rows)));
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
@@ -616,7 +631,7 @@ extern "C" int d3m_occupancy_flags(const float* occ, int64_t occ_stride, const f
   D3M_REQUIRE(occ && flags, D3M_ERR_ARG, "d3m_occupancy_flags: NULL pointer");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   LaunchScope ls("occupancy_flags", stream);
-  occupancy_flags_kernel<<<blocks_for(N, 256), 256, 0, stream>>>(occ, occ_stride, count, min_count, grid_mask,
+  launch_k(occupancy_flags_kernel, dim3(blocks_for(N, 256)), dim3(256), 0, stream, occ, occ_stride, count, min_count, grid_mask,
                                                                 threshold, N, flags);
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
@@ -645,17 +660,17 @@ extern "C" int d3m_compact(const uint8_t* flags, int64_t N, int invert, const in
   const bool al = aligned16(flags);
   {
     LaunchScope ls("compact_count", stream);
-    compact_count_kernel<<<(unsigned)chunks, CMP_THREADS, 0, stream>>>(flags, N, al, invert != 0, chunk);
+    launch_k(compact_count_kernel, dim3((unsigned)chunks), dim3(CMP_THREADS), 0, stream, flags, N, al, invert != 0, chunk);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
   {
     LaunchScope ls("compact_scan", stream);
-    compact_scan_kernel<<<1, 1024, 0, stream>>>(chunk, chunks, total_dev);
+    launch_k(compact_scan_kernel, dim3(1), dim3(1024), 0, stream, chunk, chunks, total_dev);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
   {
     LaunchScope ls("compact_write", stream);
-    compact_write_kernel<int64_t><<<(unsigned)chunks, CMP_THREADS, 0, stream>>>(flags, N, al, invert != 0, chunk, values,
+    launch_k(compact_write_kernel<int64_t>, dim3((unsigned)chunks), dim3(CMP_THREADS), 0, stream, flags, N, al, invert != 0, chunk, values,
                                                                                  out);
     D3M_CUDA_CHECK(cudaGetLastError());
   }
@@ -674,7 +689,7 @@ extern "C" int d3m_drop_ranks(const int64_t* choice, int64_t n_choice, int64_t n
   if (n_choice == 0) return D3M_OK;
   D3M_REQUIRE(choice != nullptr, D3M_ERR_ARG, "d3m_drop_ranks: choice is NULL");
   LaunchScope ls("drop_ranks", stream);
-  drop_ranks_kernel<<<blocks_for(n_choice, 256), 256, 0, stream>>>(choice, n_choice, n_keep, keep, bad);
+  launch_k(drop_ranks_kernel, dim3(blocks_for(n_choice, 256)), dim3(256), 0, stream, choice, n_choice, n_keep, keep, bad);
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
 }
@@ -690,11 +705,11 @@ extern "C" int d3m_gather_rows(const void* src, int64_t row_bytes, const int64_t
   LaunchScope ls("gather_rows", stream);
   if (row_bytes % 16 == 0 && aligned16(src) && aligned16(dst)) {
     const int v = (int)(row_bytes / 16);
-    gather_rows_kernel<uint4><<<blocks_for(M * v, 256), 256, 0, stream>>>(static_cast<const uint4*>(src), v, ind,
+    launch_k(gather_rows_kernel<uint4>, dim3(blocks_for(M * v, 256)), dim3(256), 0, stream, static_cast<const uint4*>(src), v, ind,
                                                                         M * v, static_cast<uint4*>(dst));
   } else {
     const int v = (int)(row_bytes / 4);
-    gather_rows_kernel<uint32_t><<<blocks_for(M * v, 256), 256, 0, stream>>>(static_cast<const uint32_t*>(src), v, ind,
+    launch_k(gather_rows_kernel<uint32_t>, dim3(blocks_for(M * v, 256)), dim3(256), 0, stream, static_cast<const uint32_t*>(src), v, ind,
                                                                            M * v, static_cast<uint32_t*>(dst));
   }
   D3M_CUDA_CHECK(cudaGetLastError());
@@ -724,12 +739,12 @@ extern "C" int d3m_gather_concat(const float* const* srcs_host, const int* width
   const int wtot = s.begin[n_src];
   if (wtot % 2 == 0 && (reinterpret_cast<uintptr_t>(dst) & 7u) == 0 && total / 2 < (1ll << 32) - (1 << 20)) {
     const int64_t units = total / 2;
-    gather_concat_pair_kernel<<<blocks_for(units, 256 * GC_UNROLL), 256, 0, stream>>>(
+    launch_k(gather_concat_pair_kernel, dim3(blocks_for(units, 256 * GC_UNROLL)), dim3(256), 0, stream, 
         s, ind, (uint32_t)units, (uint32_t)(wtot / 2), reinterpret_cast<float2*>(dst));
   } else if (tile_bytes <= 40 * 1024) {
-    gather_concat_tile_kernel<<<blocks_for(M, GC_ROWS), 256, tile_bytes, stream>>>(s, ind, M, dst);
+    launch_k(gather_concat_tile_kernel, dim3(blocks_for(M, GC_ROWS)), dim3(256), tile_bytes, stream, s, ind, M, dst);
   } else {
-    gather_concat_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(s, ind, total, dst);
+    launch_k(gather_concat_kernel, dim3(blocks_for(total, 256)), dim3(256), 0, stream, s, ind, total, dst);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
@@ -746,7 +761,7 @@ extern "C" int d3m_batch_counts(const void* coords, int coords_kind, int64_t N, 
   int rc = check_kind(coords_kind, coords, "d3m_batch_counts");
   if (rc) return rc;
   LaunchScope ls("batch_counts", stream);
-  D3M_DISPATCH_KIND(coords_kind, (batch_counts_kernel<K><<<blocks_for(N, 256), 256, 0, stream>>>(
+  D3M_DISPATCH_KIND(coords_kind, (launch_k(batch_counts_kernel<K>, dim3(blocks_for(N, 256)), dim3(256), 0, stream, 
                                      coords, N, B, reinterpret_cast<unsigned long long*>(counts))));
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
