@@ -119,7 +119,7 @@ __device__ __forceinline__ float corner_chain(float t00, float t01, float t10, f
   return __fmaf_rn(t11, se, __fmaf_rn(t10, sw, __fmaf_rn(t01, ne, __fmul_rn(t00, nw))));
 }
 
-template <int KIND, int G, int R, int KU>
+template <int KIND, int G, int R>
 __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams p) {
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem[];
@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
             acc[i] = make_float4(q[0], q[1], q[2], q[3]);
           }
         }
-#pragma unroll KU
+#pragma unroll 2
         for (int k = 0; k < kmax; ++k) {
           const bool on = k < cj;
           const int jj = on ? j : 0;
@@ -538,21 +538,16 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <int KIND>
-static fwd_kernel_t pick_fwd_kernel(int C, int ku_want, int& G, int& R) {
-  struct Row { int g, r, ku; fwd_kernel_t k; };
-#define D3M_FWD_ROW(g, r) {g, r, 2, bp_fwd_kernel<KIND, g, r, 2>}
-#define D3M_FWD_ROW4(g, r) {g, r, 4, bp_fwd_kernel<KIND, g, r, 4>}
+static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
+  struct Row { int g, r; fwd_kernel_t k; };
+#define D3M_FWD_ROW(g, r) {g, r, bp_fwd_kernel<KIND, g, r>}
   static const Row rows[] = {
       D3M_FWD_ROW(6, 1),  D3M_FWD_ROW(3, 2),  D3M_FWD_ROW(2, 3),                    // C = 24  (level 2)
       D3M_FWD_ROW(10, 1), D3M_FWD_ROW(5, 2),  D3M_FWD_ROW(2, 5),                    // C = 40  (level 1)
       D3M_FWD_ROW(10, 2), D3M_FWD_ROW(5, 4),  D3M_FWD_ROW(4, 5),                    // C = 80  (level 0)
       D3M_FWD_ROW(4, 1),  D3M_FWD_ROW(8, 1),  D3M_FWD_ROW(16, 1), D3M_FWD_ROW(8, 3), D3M_FWD_ROW(16, 2),
-      D3M_FWD_ROW(2, 1),  D3M_FWD_ROW(3, 1),  D3M_FWD_ROW(5, 1),
-      // deeper software pipelining of the sample loop (4 samples' corner loads in flight per lane group) for the
-      // single-wave, latency-bound launches of fragment-sized levels
-      D3M_FWD_ROW4(6, 1), D3M_FWD_ROW4(10, 1), D3M_FWD_ROW4(10, 2)};
+      D3M_FWD_ROW(2, 1),  D3M_FWD_ROW(3, 1),  D3M_FWD_ROW(5, 1)};
 #undef D3M_FWD_ROW
-#undef D3M_FWD_ROW4
   G = 0; R = 0;
   if (C % 4 != 0) return nullptr;
   const int q = C / 4;
@@ -566,28 +561,29 @@ static fwd_kernel_t pick_fwd_kernel(int C, int ku_want, int& G, int& R) {
     }
   }
   const Row* pick = nullptr;
-  for (const Row& row : rows) {  // shape first (the first ku = 2 row of that shape is the default) ...
-    if (row.g * row.r != q || row.ku != 2) continue;
+  for (const Row& row : rows) {
+    if (row.g * row.r != q) continue;
     if (!pick) pick = &row;
     if (row.g == want_g && row.r == want_r) { pick = &row; break; }
   }
   if (!pick) return nullptr;
-  for (const Row& row : rows)  // ... then the requested pipelining depth of that shape, when it is instantiated
-    if (row.g == pick->g && row.r == pick->r && row.ku == ku_want) { pick = &row; break; }
   G = pick->g; R = pick->r;
   return pick->k;
 }
 
 // Launch shape.  Large N: 32-voxel warp tiles, grid capped at 32 CTAs per SM (grid-stride).  Small N (the launch is a single
 // wave): the kernel's duration is ONE warp's latency chain -- views x projection, then tile/NG rounds of count[n] dependent
-// gather steps -- so the tile shrinks (down to D3M_FWD_TVMIN voxels, a multiple of 4 to keep the bulk store 16-byte aligned)
-// until the GPU holds D3M_FWD_WARPS_PER_SM warps per SM, and the sample loop is pipelined 4 deep (D3M_FWD_KU).
+// gather steps (ncu: 45 % of the stall samples sit on the first use of the corner loads) -- so the tile shrinks, down to
+// D3M_FWD_TVMIN voxels (a multiple of 4 keeps the bulk store 16-byte aligned), until the GPU holds D3M_FWD_WARPS_PER_SM
+// warps per SM.  Measured on the fragment step (profiles/r01j_step_variants.txt): tile floor 4 vs 8 vs 16 -> level-0
+// forward 27.7 / 33.5 / 48.2 us; 16 -> 24 / 32 warps per SM makes level 1 slower (33 vs 28 us).  Tried and dropped: a 4-deep
+// software pipeline of the sample loop (no gain) and a flattened (voxel, view) sample list with a shared-memory summation
+// pass in view order (bit-identical, but 1.5x slower: the extra pass costs more than the idle lane groups it removes).
 template <int KIND>
 static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   FwdParams p = p0;
-  static const int tv_min = env_int("D3M_FWD_TVMIN", 8);
+  static const int tv_min = env_int("D3M_FWD_TVMIN", 4);
   static const int warps_per_sm = env_int("D3M_FWD_WARPS_PER_SM", 16);
-  static const int ku_small = env_int("D3M_FWD_KU", 2);
   static const int stage_kr = env_int("D3M_FWD_STAGE_KR", 1);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -596,9 +592,8 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   int tv = 32;
   const int tv_floor = tv_min >= 4 && tv_min <= 32 && (tv_min & (tv_min - 1)) == 0 ? tv_min : 8;
   while (tv > tv_floor && (p.N + tv - 1) / tv < (int64_t)sms * warps_per_sm) tv >>= 1;
-  const bool small = tv < 32;
   int G, R;
-  fwd_kernel_t k = pick_fwd_kernel<KIND>(p.C, small ? ku_small : 2, G, R);
+  fwd_kernel_t k = pick_fwd_kernel<KIND>(p.C, G, R);
   if (!k) {
     D3M_REQUIRE(p.C <= 32 * kGenericMaxR, D3M_ERR_ARG, "back_project: C=%d unsupported (C%%4!=0 needs C<=%d)", p.C,
                 32 * kGenericMaxR);

@@ -1,6 +1,6 @@
 """Headline fragment step (3 levels, sparse coords, fwd+bwd) under a list of environment settings (run on the GPU box).
 
-    python tools/step_variants.py "" "D3M_PDL=0" "D3M_FWD_TVMIN=4,D3M_FWD_KU=4" ...
+    python tools/step_variants.py "" "D3M_PDL=0" "D3M_FWD_TVMIN=4;D3M_FWD_KU=4" ...
 
 Each variant runs in its own process (the library reads its tuning switches once).  Per variant one line:
 graph-replayed ms per step (L2 flushed between steps, like bench.py), eager ms, and per-level per-kernel device
@@ -57,7 +57,7 @@ print(json.dumps({"variant": os.environ.get("D3M_VARIANT", ""), "graph_ms(mean,m
 '''
 for var in sys.argv[1:] or [""]:
     env = dict(os.environ, D3M_VARIANT=var)
-    for kv in filter(None, var.split(",")):
+    for kv in filter(None, var.split(";")):
         k, v = kv.split("=", 1)
         env[k] = v
     subprocess.run([sys.executable, "-c", code], env=env)
