@@ -577,8 +577,9 @@ static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
 // D3M_FWD_TVMIN voxels (a multiple of 4 keeps the bulk store 16-byte aligned), until the GPU holds D3M_FWD_WARPS_PER_SM
 // warps per SM.  Measured on the fragment step (profiles/r01j_step_variants.txt): tile floor 4 vs 8 vs 16 -> level-0
 // forward 27.7 / 33.5 / 48.2 us; 16 -> 24 / 32 warps per SM makes level 1 slower (33 vs 28 us).  Tried and dropped: a 4-deep
-// software pipeline of the sample loop (no gain) and a flattened (voxel, view) sample list with a shared-memory summation
-// pass in view order (bit-identical, but 1.5x slower: the extra pass costs more than the idle lane groups it removes).
+// software pipeline of the sample loop (no gain), a flattened (voxel, view) sample list with a shared-memory summation
+// pass in view order (bit-identical, but 1.5x slower: the extra pass costs more than the idle lane groups it removes), and
+// a 4-deep cp.async ring per lane for the corner texels (bit-identical, 1.4x slower at every size).
 template <int KIND>
 static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   FwdParams p = p0;
