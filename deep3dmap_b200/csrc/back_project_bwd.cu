@@ -223,26 +223,39 @@ __global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdPar
     if (w < warp) woff += red[w];
     total += red[w];
   }
-  if (tid == 0) {
+  if (warp == 0) {
+    // decoupled look-back, one warp wide: lane l inspects chunk cid-1-l; the nearest predecessor that already holds an
+    // inclusive prefix (state 2) ends the walk, the aggregates (state 1) in front of it are summed with one shuffle tree.
+    // Ticketed chunk ids guarantee that every predecessor is running, so the spin terminates.
     volatile unsigned long long* st = p.scan_state;
     int prefix = 0;
     if (cid == 0) {
-      st[0] = (2ull << 32) | (unsigned)total;
+      if (lane == 0) st[0] = (2ull << 32) | (unsigned)total;
     } else {
-      st[cid] = (1ull << 32) | (unsigned)total;
-      __threadfence();
-      int j = cid - 1;
-      while (true) {
-        unsigned long long w;
-        do { w = st[j]; } while ((w >> 32) == 0ull);
-        prefix += (int)(unsigned)(w & 0xffffffffull);
-        if ((w >> 32) == 2ull) break;
-        --j;
+      if (lane == 0) {
+        st[cid] = (1ull << 32) | (unsigned)total;
+        __threadfence();
       }
-      st[cid] = (2ull << 32) | (unsigned)(prefix + total);
+      for (int j0 = cid - 1;; j0 -= 32) {
+        const int j = j0 - lane;
+        unsigned long long w = 2ull << 32;  // "chunk -1": inclusive prefix 0
+        if (j >= 0) {
+          do { w = st[j]; } while ((w >> 32) == 0ull);
+        }
+        const unsigned done = __ballot_sync(kFullB, (w >> 32) == 2ull);
+        const int first = __ffs(done) - 1;  // -1: no inclusive prefix in this window
+        int use = (done == 0u || lane <= first) ? (int)(unsigned)(w & 0xffffffffull) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) use += __shfl_xor_sync(kFullB, use, o);
+        prefix += use;
+        if (done != 0u) break;
+      }
+      if (lane == 0) st[cid] = (2ull << 32) | (unsigned)(prefix + total);
     }
-    s_prefix = prefix;
-    if (cid == p.nchunks - 1) p.bin_start[p.Mb] = prefix + total;
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (cid == p.nchunks - 1) p.bin_start[p.Mb] = prefix + total;
+    }
   }
   __syncthreads();
   int off = s_prefix + woff + inc - s;

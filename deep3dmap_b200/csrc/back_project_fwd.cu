@@ -43,7 +43,6 @@ struct FwdParams {
   int* cell_hist;         // optional histogram of valid samples per (bilinear cell, voxel bucket) bin, consumed by backward
   int nb_log2;            // BinCfg of this call
   int tv;
-  int stage_kr;           // 1: per-warp shared-memory staging of the projection rows (stage_krcam)
   int vchunk;
   int64_t num_tiles;
   int per_warp_bytes;
@@ -63,38 +62,16 @@ __device__ __forceinline__ void bulk_store_tile(float* gdst, const float* ssrc, 
   __syncwarp();
 }
 
-// The per-view projection rows are read by every voxel of a tile.  Loading them inside the view loop makes each warp pay
-// one dependent L2 (first touch: DRAM) round trip per view -- 9 in a row at fragment size, where one warp's latency IS the
-// kernel's duration.  Instead the warp fetches the whole chunk (3 x 128 bit per view) of its first voxel's fragment with
-// one batch of independent loads and broadcasts from shared memory; voxels of another fragment fall back to global loads.
-__device__ __forceinline__ void stage_krcam(const FwdParams& p, int bt, int v0, int v1, int lane, float4* kr_s) {
-  if (bt >= 0) {
-    const float4* KR4 = reinterpret_cast<const float4*>(p.KR);
-    for (int i = lane; i < 3 * (v1 - v0); i += 32) {
-      const int v = v0 + i / 3, r = i - 3 * (i / 3);
-      kr_s[i] = __ldg(KR4 + ((int64_t)v * p.B + bt) * 4 + r);
-    }
-  }
-  __syncwarp();
-}
-
 // phase 1 for one chunk of views; returns the number of records pushed by this lane
-// kr_s / bt: the chunk's projection rows of fragment `bt`, staged in shared memory by stage_krcam (NULL: not staged)
 template <int KIND>
 __device__ __forceinline__ int push_records(const FwdParams& p, int b, int64_t n, float gx, float gy, float gz, int v0,
-                                            int v1, int lane, int* rec_off, float* rec_fx, float* rec_fy, float& zsum,
-                                            const float4* kr_s = nullptr, int bt = -1) {
+                                            int v1, int lane, int* rec_off, float* rec_fx, float* rec_fy, float& zsum) {
   int ccnt = 0;
   if (b >= 0) {
     const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
-    const bool staged = kr_s != nullptr && b == bt;
     for (int v = v0; v < v1; ++v) {
       float4 r0, r1, r2;
-      if (staged) {
-        r0 = kr_s[3 * (v - v0)]; r1 = kr_s[3 * (v - v0) + 1]; r2 = kr_s[3 * (v - v0) + 2];
-      } else {
-        load_krcam(p.KR, v, p.B, b, r0, r1, r2);
-      }
+      load_krcam(p.KR, v, p.B, b, r0, r1, r2);
       const Sample s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
       if (s.valid) {
         int off = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
@@ -132,7 +109,6 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
   int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
   float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
   float* rec_fy = rec_fx + p.vchunk * 32;
-  float4* kr_s = p.stage_kr ? reinterpret_cast<float4*>(rec_fy + p.vchunk * 32) : nullptr;
   const float4* __restrict__ feats4 = reinterpret_cast<const float4*>(p.feats);
   if (blockIdx.x == 0 && threadIdx.x == 0) *p.counter = 0u;
 
@@ -156,9 +132,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
     for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
       const int v1 = min(p.V, v0 + p.vchunk);
       const bool first = (v0 == 0), last = (v1 == p.V);
-      const int bt = __shfl_sync(kFull, b, 0);
-      if (kr_s) stage_krcam(p, bt, v0, v1, lane, kr_s);
-      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum, kr_s, bt);
+      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
       cnt += ccnt;
       __syncwarp();
       for (int r = 0; r * NG < p.tv; ++r) {
@@ -532,11 +506,6 @@ typedef void (*fwd_kernel_t)(const FwdParams);
 
 // (G lanes x R float4 per lane) = C/4 channel quads per voxel.  The table lists every instantiated shape; for a given
 // C the FIRST matching row is the default, D3M_FWD_GR="C:G:R[,C:G:R...]" (tuning aid) selects another one.
-static int env_int(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return (e && *e) ? atoi(e) : dflt;
-}
-
 template <int KIND>
 static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
   struct Row { int g, r; fwd_kernel_t k; };
@@ -571,28 +540,14 @@ static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
   return pick->k;
 }
 
-// Launch shape.  Large N: 32-voxel warp tiles, grid capped at 32 CTAs per SM (grid-stride).  Small N (the launch is a single
-// wave): the kernel's duration is ONE warp's latency chain -- views x projection, then tile/NG rounds of count[n] dependent
-// gather steps (ncu: 45 % of the stall samples sit on the first use of the corner loads) -- so the tile shrinks, down to
-// D3M_FWD_TVMIN voxels (a multiple of 4 keeps the bulk store 16-byte aligned), until the GPU holds D3M_FWD_WARPS_PER_SM
-// warps per SM.  Measured on the fragment step (profiles/r01j_step_variants.txt): tile floor 4 vs 8 vs 16 -> level-0
-// forward 27.7 / 33.5 / 48.2 us; 16 -> 24 / 32 warps per SM makes level 1 slower (33 vs 28 us).  Tried and dropped: a 4-deep
-// software pipeline of the sample loop (no gain), a flattened (voxel, view) sample list with a shared-memory summation
-// pass in view order (bit-identical, but 1.5x slower: the extra pass costs more than the idle lane groups it removes), and
-// a 4-deep cp.async ring per lane for the corner texels (bit-identical, 1.4x slower at every size).
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 template <int KIND>
 static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   FwdParams p = p0;
-  static const int tv_min = env_int("D3M_FWD_TVMIN", 4);
-  static const int warps_per_sm = env_int("D3M_FWD_WARPS_PER_SM", 16);
-  static const int stage_kr = env_int("D3M_FWD_STAGE_KR", 1);
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  // voxels per warp tile: 32 for large N; shrink for small N so every SM still gets several warps
-  int tv = 32;
-  const int tv_floor = tv_min >= 4 && tv_min <= 32 && (tv_min & (tv_min - 1)) == 0 ? tv_min : 8;
-  while (tv > tv_floor && (p.N + tv - 1) / tv < (int64_t)sms * warps_per_sm) tv >>= 1;
   int G, R;
   fwd_kernel_t k = pick_fwd_kernel<KIND>(p.C, G, R);
   if (!k) {
@@ -600,12 +555,28 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
                 32 * kGenericMaxR);
     k = bp_fwd_generic_kernel<KIND>;
   }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // Launch shape.  Large N: 32-voxel warp tiles, grid capped at 32 CTAs per SM (grid-stride).  Small N (the launch is a
+  // single wave): the kernel's duration is ONE warp's chain -- views x projection, then tile/NG rounds of count[n] dependent
+  // gather steps -- so the tile shrinks, down to D3M_FWD_TVMIN voxels (a multiple of 4 keeps the bulk store 16-byte
+  // aligned), until the GPU holds D3M_FWD_WARPS_PER_SM warps per SM.  Measured on the fragment step
+  // (profiles/r01j_step_variants.txt): tile floor 4 / 8 / 16 -> level-0 forward 27.7 / 33.5 / 48.2 us; 24 or 32 warps per
+  // SM instead of 16 makes level 1 slower (33 vs 28 us).  Tried on top of this and dropped, all bit-identical and all
+  // slower or equal: a 4-deep software pipeline of the sample loop, staging the projection rows in shared memory,
+  // a flattened (voxel, view) sample list with an in-order shared-memory summation pass (1.5x slower), a 4-deep cp.async
+  // ring per lane for the corner texels (1.4x slower) and L1 prefetch of the corners 1-9 samples ahead (2-20 % slower):
+  // every extra load/store-unit instruction costs more than the latency it hides.
+  static const int tv_min = env_int("D3M_FWD_TVMIN", 4);
+  static const int warps_per_sm = env_int("D3M_FWD_WARPS_PER_SM", 16);
+  const int tv_floor = tv_min >= 4 && tv_min <= 32 && (tv_min & (tv_min - 1)) == 0 ? tv_min : 8;
+  int tv = 32;
+  while (tv > tv_floor && (p.N + tv - 1) / tv < (int64_t)sms * warps_per_sm) tv >>= 1;
   p.tv = tv;
-  p.stage_kr = stage_kr ? 1 : 0;
   p.vchunk = p.V < kMaxViewChunk ? p.V : kMaxViewChunk;
   p.num_tiles = (p.N + tv - 1) / tv;
-  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)3 * p.vchunk * 32 * 4 +
-                                       (size_t)p.vchunk * 48, 16);
+  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)3 * p.vchunk * 32 * 4, 16);
   const size_t smem = (size_t)p.per_warp_bytes * kFwdWarps;
   D3M_REQUIRE(smem <= 200 * 1024, D3M_ERR_ARG, "back_project: C=%d needs %zu B shared memory per CTA", p.C, smem);
   D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -615,7 +586,7 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   if (ctas < 1) ctas = 1;
   {
     LaunchScope ls("bp_fwd", stream);
-    D3M_CUDA_CHECK(launch_k(k, dim3((unsigned)ctas), dim3(kFwdWarps * 32), smem, stream, p));
+    launch_k(k, dim3((unsigned)ctas), dim3(kFwdWarps * 32), smem, stream, p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
