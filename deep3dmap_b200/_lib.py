@@ -18,7 +18,7 @@ SYMBOLS = (
     "d3m_back_project_fwd_partial", "d3m_back_project_fwd_finish",
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
     "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_rebase", "d3m_tsdf_integrate_host",
-    "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches",
+    "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches", "d3m_upload",
     # ground-truth side of the dataloader transform
     "d3m_tsdf_occupancy", "d3m_gt_recrop",
     # level glue around back_project
@@ -95,6 +95,8 @@ def lib():
     L.d3m_tsdf_download.restype = i32
     L.d3m_tsdf_last_launches.argtypes = [vp]
     L.d3m_tsdf_last_launches.restype = i32
+    L.d3m_upload.argtypes = [vp, vp, sz, vp]
+    L.d3m_upload.restype = i32
     sigs = {
         "d3m_grid_coords": [i32, i32, i32, i32, i32, vp, vp, vp],
         "d3m_upsample": [vp, i32, vp, i64, i32, i32, i32, vp, vp, vp],

@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <condition_variable>
+#include <map>
 #include <mutex>
 #include <new>
 #include <thread>
@@ -356,6 +357,7 @@ class CopyPool {
   void copy(void* dst, const void* src, size_t bytes) {
     const int nw = (int)workers_.size();
     if (nw == 0 || bytes < (256u << 10)) { memcpy(dst, src, bytes); return; }
+    std::lock_guard<std::mutex> one_caller(call_mu_);  // the job slot below is single-entry
     const size_t part = ((bytes / (size_t)(nw + 1)) + 4095) & ~(size_t)4095;
     {
       std::lock_guard<std::mutex> lk(mu_);
@@ -400,7 +402,7 @@ class CopyPool {
     }
   }
   std::vector<std::thread> workers_;
-  std::mutex mu_;
+  std::mutex mu_, call_mu_;
   std::condition_variable cv_, done_;
   char* dst_ = nullptr;
   const char* src_ = nullptr;
@@ -718,6 +720,49 @@ extern "C" int d3m_tsdf_volumes(d3m_tsdf* h, float** tsdf, float** weight, float
   if (tsdf) *tsdf = h->tsdf;
   if (weight) *weight = h->weight;
   if (color) *color = h->color;
+  return D3M_OK;
+}
+
+// ---- d3m_upload: pageable host memory -> device through a pinned two-slot ring, staged by the copy pool ----------
+namespace {
+struct UploadRing {
+  static constexpr size_t kChunk = 8u << 20;
+  unsigned char* buf[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  bool used[2] = {false, false};
+  int next = 0;  // slots alternate across calls too, so that back-to-back small uploads overlap staging and DMA
+};
+std::mutex g_upload_mu;
+std::map<int, UploadRing> g_upload_rings;  // per device
+}  // namespace
+
+extern "C" int d3m_upload(const void* host_src, void* dev_dst, size_t bytes, void* stream_) {
+  D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "d3m_upload: no CUDA device");
+  if (bytes == 0) return D3M_OK;
+  D3M_REQUIRE(host_src && dev_dst, D3M_ERR_ARG, "d3m_upload: NULL pointer");
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  int dev = 0;
+  D3M_CUDA_CHECK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_upload_mu);
+  UploadRing& r = g_upload_rings[dev];
+  if (!r.buf[0]) {
+    for (int i = 0; i < 2; ++i) {
+      D3M_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&r.buf[i]), UploadRing::kChunk, cudaHostAllocDefault));
+      D3M_CUDA_CHECK(cudaEventCreateWithFlags(&r.done[i], cudaEventDisableTiming));
+    }
+  }
+  const unsigned char* src = static_cast<const unsigned char*>(host_src);
+  unsigned char* dst = static_cast<unsigned char*>(dev_dst);
+  for (size_t off = 0; off < bytes; off += UploadRing::kChunk) {
+    const int slot = r.next;
+    r.next ^= 1;
+    const size_t n = bytes - off < UploadRing::kChunk ? bytes - off : UploadRing::kChunk;
+    if (r.used[slot]) D3M_CUDA_CHECK(cudaEventSynchronize(r.done[slot]));  // the DMA that last read this slot
+    CopyPool::get().copy(r.buf[slot], src + off, n);
+    D3M_CUDA_CHECK(cudaMemcpyAsync(dst + off, r.buf[slot], n, cudaMemcpyHostToDevice, stream));
+    D3M_CUDA_CHECK(cudaEventRecord(r.done[slot], stream));
+    r.used[slot] = true;
+  }
   return D3M_OK;
 }
 

@@ -11,7 +11,7 @@ caller loop around `TSDFVolume.integrate` and the files it leaves on disk.
 
 Same names, argument order, file names, pickle payloads and array layouts as the reference, so a tree written here is
 consumed unchanged by the reference's `ScanNetDataset`, and vice versa.  What differs is where the time goes:
-  * all frames of a scene are staged once (pinned, in slices of `FRAMES_PER_UPLOAD`) and every volume integrates a
+  * all frames of a scene are uploaded once (`d3m_upload`, in slices of `FRAMES_PER_UPLOAD`) and every volume integrates a
     slice with ONE launch (`TSDFVolume.integrate_batch`; bit-identical to the per-frame loop because the kernel
     applies frames in order per voxel), instead of `n_frames x num_layers` launches with 7 host<->device copies each;
   * the .npz volumes are deflated chunk-parallel (`npzio.savez_compressed`) while the next level downloads.
@@ -27,7 +27,7 @@ import numpy as np
 from . import npzio
 from .tsdf import TSDFVolume, get_view_frustum
 
-FRAMES_PER_UPLOAD = 256        # 256 x 480 x 640 fp32 = 315 MB of pinned staging per slice
+FRAMES_PER_UPLOAD = 256        # 256 x 480 x 640 fp32 = 315 MB of device memory per slice (two slices in flight)
 BOUNDS_MAX_FRAMES = 200        # tools/data_gen/scannet.py:58-60
 
 
@@ -71,8 +71,14 @@ def _integrate_all(volumes, cam_intr, depth_list, cam_pose_list, color_list, fra
         return len(ids) * len(volumes)
     h, w = depth_list[ids[0]].shape
     n_slice = min(len(ids), int(frames_per_upload))
-    stage = [torch.empty((n_slice, h, w), dtype=torch.float32).pin_memory() for _ in range(2)]
+    # frames go straight from the caller's (pageable) arrays into the device slice through d3m_upload: the library's copy
+    # threads stage each 1.2 MB frame into a pinned ring while the previous one is on the copy engine -- no 2 x 315 MB
+    # pinned staging tensors, no single-threaded frame-by-frame memcpy
+    from . import _lib
+    from .voxel import _stream
+    L = _lib.lib()
     dev = [torch.empty((n_slice, h, w), dtype=torch.float32, device="cuda") for _ in range(2)]
+    stream = _stream(dev[0].device)
     done = [None, None]
     launches = 0
     for s, lo in enumerate(range(0, len(ids), n_slice)):
@@ -80,14 +86,12 @@ def _integrate_all(volumes, cam_intr, depth_list, cam_pose_list, color_list, fra
         k = s & 1
         if done[k] is not None:
             done[k].synchronize()        # the launches that read dev[k] two slices ago
-        buf = stage[k].numpy()
         for j, fid in enumerate(part):
-            d = depth_list[fid]
+            d = np.ascontiguousarray(depth_list[fid], dtype=np.float32)
             if d.shape != (h, w):
                 raise ValueError("all depth frames of a scene must share one shape")
-            buf[j] = d
+            _lib.check(L.d3m_upload(d.ctypes.data, dev[k][j].data_ptr(), d.nbytes, stream), "d3m_upload")
         poses = np.stack([np.asarray(cam_pose_list[fid]) for fid in part])
-        dev[k][:len(part)].copy_(stage[k][:len(part)], non_blocking=True)
         for v in volumes:
             v.integrate_batch(dev[k][:len(part)], cam_intr, poses, obs_weights=1.)
             launches += 1

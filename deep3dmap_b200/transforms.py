@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 from .tsdf import TSDFVolumeTorch
-from .voxel import _on_device, _stream
+from .voxel import _on_device, _stream, upload
 
 _f32x3 = ctypes.c_float * 3
 _f32x12 = ctypes.c_float * 12
@@ -210,7 +210,7 @@ class SeqRandomTransformSpace(object):
             _lib.require_device()
             dev = torch.device("cuda", torch.cuda.current_device() if self.device is None else int(self.device))
             old_origin = old_origin.view(1, 3)
-            depth = torch.as_tensor(data[self.in_depth_key]).float().to(dev, non_blocking=True)
+            depth = upload(torch.as_tensor(data[self.in_depth_key]).float(), dev)
             n_views = data[self.in_imgs_key].shape[0]
             intr = torch.stack([torch.as_tensor(data[self.in_intrinsics_key][i]).float() for i in range(n_views)])
             poses = [torch.as_tensor(data[self.in_extrinsics_key][i]) for i in range(n_views)]
@@ -224,7 +224,7 @@ class SeqRandomTransformSpace(object):
                 t_dev, w_dev = vol.device_volumes()
                 occ_vol = tsdf_occupancy(t_dev, w_dev)
                 # ------ scene tsdf re-sampled on the fragment grid (:368-396) ------
-                full = torch.as_tensor(tsdf_s).float().to(dev, non_blocking=True)
+                full = upload(torch.as_tensor(tsdf_s).float(), dev)
                 tsdf_vol = gt_recrop(full, self.voxel_dim, self.voxel_size, vol_origin_partial, transform, old_origin, l)
                 if not self.keep_on_device:
                     tsdf_vol, occ_vol = tsdf_vol.cpu(), occ_vol.cpu()

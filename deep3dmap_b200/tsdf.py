@@ -163,7 +163,10 @@ class TSDFVolume:
         keep = []
         if isinstance(depth_ims, np.ndarray):
             import torch
-            d = torch.from_numpy(np.ascontiguousarray(depth_ims, dtype=np.float32)).cuda(non_blocking=False)
+            from .voxel import upload
+            d = upload(torch.from_numpy(np.ascontiguousarray(depth_ims, dtype=np.float32)),
+                       torch.device("cuda", torch.cuda.current_device()))
+            torch.cuda.current_stream().synchronize()  # the handle's stream need not be torch's current one
             keep.append(d)
         else:
             d = depth_ims

@@ -7,6 +7,8 @@ the hand-written sm_100a kernels of `libd3m.so` (forward: `csrc/back_project_fwd
 backward w.r.t. `feats`: `csrc/back_project_bwd.cu`).  PyTorch only provides device memory, the
 current stream and the autograd hook.  There is no fallback path: CPU tensors raise.
 """
+import os
+
 import torch
 
 from . import _lib
@@ -22,8 +24,33 @@ def _ptr(t):
     return t.data_ptr() if t is not None and t.numel() > 0 else None
 
 
+# `torch.cuda.current_stream(dev).cuda_stream` builds a Python Stream object (~9 us, three times per fwd+bwd);
+# the raw query is the same value in ~0.3 us.  Falls back to the public API when the private entry point is missing.
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream(device):
+    if _raw_stream is not None:
+        idx = device.index
+        return _raw_stream(torch.cuda.current_device() if idx is None else idx)
     return torch.cuda.current_stream(device).cuda_stream
+
+
+_NO_UPLOAD = os.environ.get("D3M_UPLOAD", "1") == "0"   # A/B switch: plain `.to()` for every host tensor
+
+
+def upload(t, device):
+    """CPU tensor -> CUDA tensor on the current stream.  Pageable tensors of 1 MiB and more go through `d3m_upload`
+    (chunked, staged by the library's copy threads into a pinned ring: ~3x the rate of a plain `.to()`)."""
+    t = t.contiguous()
+    nbytes = t.numel() * t.element_size()
+    if t.is_cuda or nbytes < (1 << 20) or t.is_pinned() or _NO_UPLOAD:
+        return t.to(device, non_blocking=True)
+    out = torch.empty(t.shape, dtype=t.dtype, device=device)
+    with _on_device(out.device):
+        rc = _lib.lib().d3m_upload(t.data_ptr(), out.data_ptr(), nbytes, _stream(out.device))
+    _lib.check(rc, "d3m_upload")
+    return out
 
 
 class _on_device:

@@ -182,6 +182,14 @@ int d3m_tsdf_download(d3m_tsdf* h, float* tsdf_host, float* weight_host, float* 
  * tile launches of the last call (diagnostics for bench.py's gpu_launches) */
 int d3m_tsdf_last_launches(d3m_tsdf* h);
 
+/* Host (pageable) -> device copy of `bytes` bytes, stream-ordered on `stream`.  The frames and scene volumes of this path
+ * arrive as pageable numpy / torch CPU memory (tools/data_gen/scannet.py:84-100 hands cv2 frames to integrate();
+ * datasets/pipelines/transforms_seq.py:343-396 hands `tsdf_list_full`), for which a plain cudaMemcpy is a single-threaded
+ * staging copy (~10 GB/s).  Here the buffer is cut into chunks that a small thread pool copies into a two-slot pinned ring
+ * while the previous chunk is in flight on the copy engine.  Returns when the last chunk is staged: `host_src` may be
+ * reused at once, the data is in `dev_dst` for everything ordered after the call on `stream`. */
+int d3m_upload(const void* host_src, void* dev_dst, size_t bytes, void* stream);
+
 /* =============================================================================================
  * SURVEY section 8 row f1, ground-truth side of the dataloader transform
  * (deep3dmap/datasets/pipelines/transforms_seq.py:343-398, SeqRandomTransformSpace.transform).
