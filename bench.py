@@ -900,6 +900,11 @@ def bench_gt_transform(torch, dev, _lib, flush_buf, peak_gbs, reps=5, with_cpu=T
 
     torch.manual_seed(1)
     tr = SeqRandomTransformSpace([96, 96, 96], vs, max_epoch=8)
+    # The transform runs in DataLoader worker processes, which torch starts with torch.set_num_threads(1)
+    # (torch/utils/data/_utils/worker.py); with the main process's 16 intra-op threads the OpenMP workers of the small CPU
+    # ops spin on every core and slow the library's staging-copy threads 3x (tools/upload_probe_gaps.py).
+    n_thr = torch.get_num_threads()
+    torch.set_num_threads(1)
     for _ in range(2):
         out = tr(data_dict())
     torch.cuda.synchronize()
@@ -917,6 +922,7 @@ def bench_gt_transform(torch, dev, _lib, flush_buf, peak_gbs, reps=5, with_cpu=T
         for k, v in _lib.profile_end().items():
             e = acc.setdefault(k, {"n": 0, "ms": 0.0})
             e["n"] += v["n"]; e["ms"] += v["ms"]
+    torch.set_num_threads(n_thr)
     launches = (_lib.kernel_launches() - l0) // reps
     kern_us = {k: round(v["ms"] / reps * 1e3, 2) for k, v in sorted(acc.items())}
     n_out = sum((96 >> l) ** 3 for l in range(3))
@@ -926,6 +932,7 @@ def bench_gt_transform(torch, dev, _lib, flush_buf, peak_gbs, reps=5, with_cpu=T
     res = {"sample": "9 views 480x640 -> 96^3/48^3/24^3 fragment GT; scene tsdf 300x260x90 @ 4 cm (+2 coarser levels)",
            "ms_per_sample_wall": float(np.mean(wall)), "samples_per_s": 1e3 / float(np.mean(wall)),
            "ms_kernels_sum": sum(v["ms"] for v in acc.values()) / reps, "gpu_launches_per_sample": int(launches),
+           "torch_cpu_threads": 1,
            "h2d_bytes_per_sample": int(depth.nbytes + sum(t.nbytes for t in full)),
            "d2h_bytes_per_sample": int(n_out * 5), "kernel_us": kern_us,
            "occupied_voxels": [int(o.sum()) for o in out["occ_list"]],

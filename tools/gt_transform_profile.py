@@ -13,6 +13,7 @@ def data():
     return {"vol_origin": np.array([0.0, 0.0, -0.2], dtype=np.float32), "epoch": [3],
             "tsdf_list_full": [torch.from_numpy(t) for t in full], "extrinsics": torch.from_numpy(np.stack([pose] * V)).clone(),
             "intrinsics": torch.from_numpy(np.stack([K] * V)), "imgs": torch.zeros((V, 3, H, W)), "depth": torch.from_numpy(depth)}
+torch.set_num_threads(int(os.environ.get('TORCH_THREADS', '1')))   # DataLoader workers run with 1
 tr = SeqRandomTransformSpace([96, 96, 96], 0.04, max_epoch=8)
 for _ in range(3): tr(data())
 ds = [data() for _ in range(10)]
