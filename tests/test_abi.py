@@ -62,3 +62,6 @@ def test_no_device_means_loud_failure():
         TSDFVolume(np.array([[0, 1.0], [0, 1.0], [0, 1.0]]), 0.1)
     with pytest.raises(NotImplementedError):
         TSDFVolume(np.array([[0, 1.0], [0, 1.0], [0, 1.0]]), 0.1, use_gpu=False)
+    from deep3dmap_b200 import _lib
+    buf = np.zeros(16, np.uint8)
+    assert _lib.lib().d3m_upload(buf.ctypes.data, buf.ctypes.data, 16, None) != 0   # D3M_ERR_NO_DEVICE, no host copy
