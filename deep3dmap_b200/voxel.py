@@ -161,15 +161,23 @@ def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam, cell_his
 
 
 def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, grad_out, nchw=False, count=None,
-                          cell_hist=None):
+                          cell_hist=None, out=None):
     """Kernel-level backward: grad_out (N,C+1) -> grad of the maps, channels-last (V,B,H,W,C) or, with
     nchw=True, in the reference layout (V,B,C,H,W) written directly by the gather kernel.  `count` / `cell_hist`
-    from the forward pass of the same inputs are optional shortcuts (recomputed when None; same bits either way)."""
+    from the forward pass of the same inputs are optional shortcuts (recomputed when None; same bits either way);
+    `out` receives the result in place of a fresh tensor."""
     L = _lib.lib()
     dev = grad_out.device
     V, B, H, W, C = feats_shape_nhwc
     N = coords.shape[0]
-    grad = torch.empty((V, B, C, H, W) if nchw else (V, B, H, W, C), dtype=torch.float32, device=dev)
+    shape = (V, B, C, H, W) if nchw else (V, B, H, W, C)
+    if out is not None:
+        # caller-provided destination (e.g. a view range of a larger gradient tensor, shard.py)
+        if tuple(out.shape) != shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+            raise ValueError("back_project_backward: `out` must be a contiguous float32 %s tensor on %s" % (shape, dev))
+        grad = out
+    else:
+        grad = torch.empty(shape, dtype=torch.float32, device=dev)
     if grad.numel() == 0:
         return grad
     ws, ws_bytes = _workspace("b", (N, B, V, C, H, W), dev)

@@ -62,6 +62,29 @@ def test_sharded_autograd_function_world1_equals_back_project():
     assert torch.equal(v1, v2) and torch.equal(c1, c2) and torch.equal(f1.grad, f2.grad)
 
 
+@pytest.mark.parametrize("level,n", [(2, 20000), (0, 5000)])
+def test_view_range_backward_is_bit_identical_to_one_call(level, n):
+    """shard.py all-reduces grad_feats per view range while the next range is computed: the ranges must reproduce the
+    single backward call bit for bit (with and without the forward histogram; uneven and single-view ranges)."""
+    dev = torch.device("cuda:0")
+    inp = cases.bp_level(level, n, np.int64)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    ops = shard._CudaLocalOps
+    feats = t(inp["feats"])
+    V, B, C, H, W = feats.shape
+    out, cnt, sums, state = ops.forward_partial(t(inp["coords"]), t(inp["origin"]), inp["voxel_size"], feats,
+                                                t(inp["KRcam"]), want_hist=True)
+    go = t(inp["grad_out"])
+    ref = ops.backward(state, inp["voxel_size"], go, cnt)
+    for chunks in ([(0, 2), (2, 3), (3, V)], [(0, V // 2), (V // 2, V)], [(v, v + 1) for v in range(V)]):
+        for st in (state, state[:6] + (None,)):           # with / without the forward-pass histogram
+            grad = torch.full((V, B, C, H, W), float("nan"), device=dev)
+            for v0, v1 in chunks:
+                ops.backward_views(st, inp["voxel_size"], go, cnt, v0, v1, grad[v0:v1])
+            assert torch.equal(grad, ref), (chunks, st[6] is None)
+    assert shard.grad_view_chunks(64, 1) == [(0, 64)] and shard.grad_view_chunks(5, 8) == [(0, 5)]
+
+
 def test_tsdf_x_slabs_concatenate_to_full_volume():
     from deep3dmap_b200 import TSDFVolume
     c = cases.tsdf_case("orbit_small")
