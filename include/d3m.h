@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 103
+#define D3M_VERSION 104
 
 enum {
   D3M_OK = 0,
