@@ -745,11 +745,9 @@ extern "C" int d3m_upload(const void* host_src, void* dev_dst, size_t bytes, voi
   D3M_CUDA_CHECK(cudaGetDevice(&dev));
   std::lock_guard<std::mutex> lk(g_upload_mu);
   UploadRing& r = g_upload_rings[dev];
-  if (!r.buf[0]) {
-    for (int i = 0; i < 2; ++i) {
-      D3M_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&r.buf[i]), UploadRing::kChunk, cudaHostAllocDefault));
-      D3M_CUDA_CHECK(cudaEventCreateWithFlags(&r.done[i], cudaEventDisableTiming));
-    }
+  for (int i = 0; i < 2; ++i) {  // lazily, and per slot: a failed allocation leaves the ring consistent for the next call
+    if (!r.buf[i]) D3M_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&r.buf[i]), UploadRing::kChunk, cudaHostAllocDefault));
+    if (!r.done[i]) D3M_CUDA_CHECK(cudaEventCreateWithFlags(&r.done[i], cudaEventDisableTiming));
   }
   const unsigned char* src = static_cast<const unsigned char*>(host_src);
   unsigned char* dst = static_cast<unsigned char*>(dev_dst);
