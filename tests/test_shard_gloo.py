@@ -55,6 +55,36 @@ class OracleLocalOps:
         return torch.from_numpy(oracle.back_project_bwd(c, o, voxel_size, shape, k, grad_out.numpy()))
 
 
+class OracleLocalOpsViews(OracleLocalOps):
+    """Adds the view-range backward (shard._CudaLocalOps.backward_views), so that the per-range all-reduce path of
+    `_BackProjectVoxelSharded.backward` runs under gloo; state[2] is the (V,B,H,W,C) shape shard.py reads."""
+
+    @staticmethod
+    def forward_partial(coords, origin, voxel_size, feats, KRcam, want_hist=False):
+        vol, cnt, sums, (c, o, k, fs) = OracleLocalOps.forward_partial(coords, origin, voxel_size, feats, KRcam, want_hist)
+        V, B, C, H, W = fs
+        return vol, cnt, sums, (c, o, (V, B, H, W, C), k, fs)
+
+    @staticmethod
+    def forward_finish(out, sums, state):
+        return OracleLocalOps.forward_finish(out, sums, (state[0], state[1], state[3], state[4]))
+
+    @staticmethod
+    def backward(state, voxel_size, grad_out, count):
+        return OracleLocalOps.backward((state[0], state[1], state[3], state[4]), voxel_size, grad_out, count)
+
+    @staticmethod
+    def backward_views(state, voxel_size, grad_out, count, v0, v1, out):
+        c, o, _, k, (V, B, C, H, W) = state
+        ks = np.ascontiguousarray(k[v0:v1])
+        # the oracle divides by the view count of the views it is given; the contract divides by the count over ALL views
+        _, cs = oracle.back_project_fwd(c, o, voxel_size, np.zeros((v1 - v0, B, C, H, W), np.float32), ks)
+        scale = (np.maximum(cs, 1.0) / np.maximum(count.numpy(), 1.0)).astype(np.float32)
+        g = oracle.back_project_bwd(c, o, voxel_size, (v1 - v0, B, C, H, W), ks, grad_out.numpy() * scale[:, None])
+        out.copy_(torch.from_numpy(g))
+        return out
+
+
 def _free_port():
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -99,7 +129,17 @@ def _worker(rank, world, port, ret):
         g = [torch.empty_like(feats.grad) for _ in range(world)]
         dist.all_gather(g, feats.grad)
         assert torch.equal(g[0], g[1])
-        # ---- a rank whose slice got no gradient must still join the all-reduce ----------------------
+        # ---- grad_feats all-reduced per view range (D3M_SHARD_GRAD_CHUNKS) == one all-reduce ---------------
+        os.environ["D3M_SHARD_GRAD_CHUNKS"] = "2"
+        assert len(shard.grad_view_chunks(inp["feats"].shape[0], world)) == 2
+        feats2 = torch.from_numpy(inp["feats"]).requires_grad_(True)
+        vol2, _ = shard.back_project_voxel_sharded(torch.from_numpy(inp["coords"][b:e]), torch.from_numpy(inp["origin"]),
+                                                   inp["voxel_size"], feats2, torch.from_numpy(inp["KRcam"]),
+                                                   local_ops=OracleLocalOpsViews)
+        vol2.backward(torch.from_numpy(inp["grad_out"][b:e]))
+        os.environ["D3M_SHARD_GRAD_CHUNKS"] = "1"
+        assert torch.equal(vol2.detach(), vol.detach())
+        assert_close(feats2.grad.numpy(), o_grad, "grad_feats all-reduced per view range")
         ret[rank] = "ok"
     except Exception as err:  # surface the failure in the parent
         import traceback
