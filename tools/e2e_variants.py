@@ -115,6 +115,39 @@ def main():
             main_s.synchronize()
         return f
 
+    out_streams = [torch.cuda.Stream(device=dev) for _ in pin]
+
+    def phased_split(order_fwd, order_bwd):
+        """like `phased`, but every level reads its results back on a second stream, so that the level's next upload
+        (grad_out) is not queued behind its own volume read-back"""
+        def f():
+            main_s = torch.cuda.current_stream()
+            keep = {}
+            for i in order_fwd:
+                hp, st, so = pin[i], streams[i], out_streams[i]
+                st.wait_stream(main_s); so.wait_stream(main_s)
+                with torch.cuda.stream(st):
+                    c = hp["coords"].to(dev, non_blocking=True); o = hp["origin"].to(dev, non_blocking=True)
+                    ft = hp["feats"].to(dev, non_blocking=True).requires_grad_(True); k = hp["KRcam"].to(dev, non_blocking=True)
+                    vol, cnt = back_project(c, o, hp["vs"], ft, k)
+                so.wait_stream(st)
+                with torch.cuda.stream(so):
+                    hp["o_vol"].copy_(vol.detach(), non_blocking=True); hp["o_cnt"].copy_(cnt, non_blocking=True)
+                keep[i] = (vol, ft, cnt)
+            for i in order_bwd:
+                hp, st, so = pin[i], streams[i], out_streams[i]
+                with torch.cuda.stream(st):
+                    g = hp["grad_out"].to(dev, non_blocking=True)
+                    vol, ft, _ = keep[i]
+                    vol.backward(g)
+                so.wait_stream(st)
+                with torch.cuda.stream(so):
+                    hp["o_grad"].copy_(ft.grad, non_blocking=True)
+            for st in streams + out_streams:
+                main_s.wait_stream(st)
+            main_s.synchronize()
+        return f
+
     def single_stream():
         for hp in pin:
             level_whole(hp)
@@ -125,6 +158,9 @@ def main():
                 ("phased fwd 0,1,2 / bwd 2,1,0", phased([0, 1, 2], [2, 1, 0])),
                 ("phased fwd 0,1,2 / bwd 0,1,2", phased([0, 1, 2], [0, 1, 2])),
                 ("phased fwd 2,1,0 / bwd 2,1,0", phased([2, 1, 0], [2, 1, 0])),
+                ("phased 2,1,0 / 2,1,0 + read-back streams", phased_split([2, 1, 0], [2, 1, 0])),
+                ("phased 2,1,0 / 0,1,2 + read-back streams", phased_split([2, 1, 0], [0, 1, 2])),
+                ("phased fwd 2,1,0 / bwd 2,1,0 (again)", phased([2, 1, 0], [2, 1, 0])),
                 ("single stream", single_stream)]
     for name, f in variants:
         for _ in range(3):
