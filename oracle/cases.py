@@ -88,6 +88,7 @@ BP_CASES = {
     "L1_sparse_c40_i64": lambda: bp_level(1, 6000, np.int64),
     "L2_sparse_c24_i64": lambda: bp_level(2, 9000, np.int64),
     "L2_b2_c24_f32": lambda: bp_level(2, 5000, np.float32, batch=2),
+    "L1_b3_c40_i32": lambda: bp_level(1, 7000, np.int32, batch=3),
 }
 # cases whose inputs are small enough to be stored in the fixture next to the outputs
 BP_STORE_INPUTS = ("tiny_f32", "tiny_i64", "tiny_i32", "edge")

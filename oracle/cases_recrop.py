@@ -3,7 +3,7 @@
 (which runs the unmodified reference class on them) and `tests/`."""
 import numpy as np
 
-CASES = ("rot_trans", "identity", "rot_only_edge")
+CASES = ("rot_trans", "identity", "rot_only_edge", "trans_only", "rot_trans_late")
 
 
 def _scene_tsdf(dims, voxel_size, origin, trunc):
@@ -48,7 +48,9 @@ def recrop_case(name):
         depths.append(d)
     opts = dict(rot_trans=dict(random_rotation=True, random_translation=True, epoch=3),
                 identity=dict(random_rotation=False, random_translation=False, epoch=0),
-                rot_only_edge=dict(random_rotation=True, random_translation=False, epoch=7, paddingXY=2.5))[name]
+                rot_only_edge=dict(random_rotation=True, random_translation=False, epoch=7, paddingXY=2.5),
+                trans_only=dict(random_rotation=False, random_translation=True, epoch=5),
+                rot_trans_late=dict(random_rotation=True, random_translation=True, epoch=12, paddingXY=0.5))[name]
     return dict(voxel_dim=voxel_dim, voxel_size=voxel_size, vol_origin=scene_origin, tsdf_full=tsdf_full,
                 intrinsics=np.stack([K] * V), extrinsics=np.stack(poses), depth=np.stack(depths),
                 imgs_shape=(V, 3, H, W), torch_seed=900 + seed, **opts)

@@ -36,6 +36,8 @@ def main():
     mod = ref_loader.transforms_seq_module()
     tsdf_mod = ref_loader.tsdf_module()
     for name in cases_recrop.CASES:
+        if os.path.exists(os.path.join(OUT, "recrop_%s.npz" % name)) and "--force" not in sys.argv:
+            continue                      # recorded fixtures are kept; --force re-records all of them
         case = cases_recrop.recrop_case(name)
         torch.manual_seed(case["torch_seed"])
         tr = mod.SeqRandomTransformSpace(case["voxel_dim"], case["voxel_size"], **ctor_kwargs(case))
