@@ -23,7 +23,16 @@ def _rigid(rng):
     return M.astype(np.float32)
 
 
-def c2f_case(seed=21):
+# recorded NeuConNet.forward runs: fixture name -> (seed of the inputs, numpy seed consumed by the reference's subsampling)
+C2F_CASES = {"c2f_levels": (21, 4321), "c2f_levels_s2": (58, 977)}
+
+
+def c2f_case(name="c2f_levels"):
+    seed, np_seed = C2F_CASES[name]
+    return _c2f_case(seed, np_seed)
+
+
+def _c2f_case(seed, np_seed):
     """Two fragments through the three coarse-to-fine levels (FUSION_ON False -> get_target is used), training mode
     with caps small enough that the random subsampling of neucon_network.py:189-194 triggers."""
     rng = np.random.default_rng(seed)
@@ -57,7 +66,7 @@ def c2f_case(seed=21):
     inputs = dict(proj_matrices=proj, vol_origin_partial=origin, world_to_aligned_camera=w2ac,
                   tsdf_list=tsdf_list, occ_list=occ_list)
     return dict(cfg=cfg, features=features, inputs=inputs, conv_w=conv_w, tsdf_lin=tsdf_lin, occ_lin=occ_lin,
-                np_seed=4321, B=B, V=V, C=C, ch_out=ch_out)
+                np_seed=np_seed, B=B, V=V, C=C, ch_out=ch_out)
 
 
 def stub_gru(h, x):

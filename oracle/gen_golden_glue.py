@@ -31,8 +31,15 @@ def _np(t):
 
 
 def gen_c2f():
+    for name in cases_glue.C2F_CASES:
+        if os.path.exists(os.path.join(OUT, name + ".npz")) and "--force" not in sys.argv:
+            continue                      # recorded fixtures are kept; --force re-records all of them
+        _gen_c2f(name)
+
+
+def _gen_c2f(name):
     nn_mod, _ = ref_loader.neucon_modules()
-    case = cases_glue.c2f_case()
+    case = cases_glue.c2f_case(name)
     cfg = case["cfg"]
     rec = {}
     level = {"i": -1}
@@ -102,7 +109,7 @@ def gen_c2f():
     # feature rows' checksum here
     for i in range(3):
         rec["L%d_volume_colsum" % i] = rec.pop("L%d_volume" % i).astype(np.float64).sum(0)
-    path = os.path.join(OUT, "c2f_levels.npz")
+    path = os.path.join(OUT, name + ".npz")
     np.savez_compressed(path, **rec)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB ; N per level",
           [rec["L%d_up_coords" % i].shape[0] for i in range(3)], "-> out", rec["out_coords"].shape[0])

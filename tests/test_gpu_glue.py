@@ -22,8 +22,9 @@ def _d(torch, a):
 
 
 # ------------------------------------------------------------------------------------------------------------ f2
-def test_level_glue_matches_reference_run():
-    util_glue.check_c2f_levels(util_glue.CudaBackend())
+@pytest.mark.parametrize("name", list(cases_glue.C2F_CASES))
+def test_level_glue_matches_reference_run(name):
+    util_glue.check_c2f_levels(util_glue.CudaBackend(), name)
 
 
 @pytest.mark.parametrize("n_vox,interval,bs", [((96, 96, 96), 4, 1), ((96, 96, 96), 1, 1), ((30, 17, 9), 4, 3),

@@ -7,8 +7,9 @@ import util_glue
 from oracle import cases_glue, glue
 
 
-def test_level_glue_matches_reference_run():
-    util_glue.check_c2f_levels(util_glue.OracleBackend())
+@pytest.mark.parametrize("name", list(cases_glue.C2F_CASES))
+def test_level_glue_matches_reference_run(name):
+    util_glue.check_c2f_levels(util_glue.OracleBackend(), name)
 
 
 def _make_oracle(case):

@@ -68,11 +68,11 @@ class CudaBackend:
         return None if r is None else (r["pre_coords"].cpu().numpy(), r["pre_feat"].cpu().numpy())
 
 
-def check_c2f_levels(be):
-    """Walk the three levels of the recorded NeuConNet.forward run (tests/golden/c2f_levels.npz): every glue step is
+def check_c2f_levels(be, name="c2f_levels"):
+    """Walk the three levels of a recorded NeuConNet.forward run (tests/golden/<name>.npz): every glue step is
     fed the reference's own intermediate tensors and must reproduce the reference's next tensors."""
-    g = load_golden("c2f_levels")
-    case = cases_glue.c2f_case()
+    g = load_golden(name)
+    case = cases_glue.c2f_case(name)
     cfg, inp = case["cfg"], case["inputs"]
     B = case["B"]
     np.random.seed(case["np_seed"])          # the subsampling consumes the global generator, like the reference
