@@ -183,29 +183,218 @@ def cpu_baseline_tsdf(n_frames=3):
     return n_frames / t, oracle.num_threads()
 
 
+def fragment_config(levels, S_levels=None, world=1):
+    """`config` of the JSON line -- the SAME keys and values on both arms (the driver compares them)."""
+    samples = sum(l["coords"].shape[0] for l in levels) * synth.N_VIEWS
+    return {"workload": WORKLOAD, "levels_N": [int(l["coords"].shape[0]) for l in levels],
+            "views": synth.N_VIEWS, "channels": [80, 40, 24], "coords_dtype": ["float32", "int64", "int64"],
+            "samples_per_step": int(samples), "fragments_per_gpu": 1,
+            "parallelism": "fragment-parallel (one fragment per GPU, no data-path collective)",
+            "l2": "256 MiB buffer written between timed steps (L2 flush); per-step CUDA events"}
+
+
+def torch_levels(levels, device):
+    """Torch tensors of the fragment's three back_project calls on `device` (reference-function arguments)."""
+    import torch
+    out = []
+    for inp in levels:
+        out.append(dict(coords=torch.from_numpy(np.ascontiguousarray(inp["coords"])).to(device),
+                        origin=torch.from_numpy(inp["origin"]).to(device), vs=inp["voxel_size"],
+                        feats=torch.from_numpy(inp["feats"]).to(device).requires_grad_(True),
+                        KR=torch.from_numpy(inp["KRcam"]).to(device), go=torch.from_numpy(inp["grad_out"]).to(device)))
+    return out
+
+
+def reference_step(tl, bp):
+    """One step through the UNMODIFIED reference function: forward + autograd backward at the three levels."""
+    for d in tl:
+        d["feats"].grad = None
+        vol, cnt = bp(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+        vol.backward(d["go"])
+
+
+def cpu_reference_bp(levels, steps, warmup):
+    """The reference's own CPU path: oracle/_ref/back_project.py (byte-for-byte copy of the reference file) executed by
+    torch on all host cores; `.cuda()` is shimmed to the identity for the duration of the calls.  -> (samples/s, s/step,
+    threads) or None when the staged file is absent."""
+    from oracle import ref_gpu
+    if not ref_gpu.have_back_project():
+        return None
+    import torch
+    n = os.cpu_count() or 1
+    torch.set_num_threads(n)   # torchrun exports OMP_NUM_THREADS=1
+    bp = ref_gpu.back_project_fn()
+    tl = torch_levels(levels, "cpu")
+    ts = []
+    with ref_gpu.cpu_shim():
+        for _ in range(max(0, warmup)):
+            reference_step(tl, bp)
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            reference_step(tl, bp)
+            ts.append(time.perf_counter() - t0)
+    samples = sum(l["coords"].shape[0] for l in levels) * synth.N_VIEWS
+    sec = sum(ts) / len(ts)
+    return samples / sec, sec, torch.get_num_threads()
+
+
 def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU implementation of the path on this box's host cores, EXACTLY
+    `--steps` timed steps after `--warmup` untimed ones, same workload / config / metric as our arm.  The implementation
+    is the unmodified reference file staged in oracle/_ref/ (kind "reference"); only when that file is absent does the
+    arm fall back to the OpenMP C port of the same algorithm (kind "port")."""
     if rank != 0:
         return
     import oracle
     levels = build_fragment_levels(oracle_count_fn(oracle))
-    steps = max(1, min(args.steps, 10))
-    v, sec, cores = cpu_baseline_bp(levels, steps, min(args.warmup, 2))
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    ref = cpu_reference_bp(levels, steps, warmup)
+    port_v, port_sec, port_cores = cpu_baseline_bp(levels, min(steps, 5), 1)
+    if ref is not None:
+        v, sec, cores = ref
+        kind = "reference"
+        sample = ("%d full steps of the same 3-level fragment through the unmodified reference back_project.py (torch "
+                  "%s CPU ops + autograd, %d threads); OpenMP C port of the same algorithm alongside: %.1f ms/step"
+                  % (steps, __import__("torch").__version__, cores, port_sec * 1e3))
+    else:
+        v, sec, cores = cpu_baseline_bp(levels, steps, warmup)
+        kind = "port"
+        sample = "%d full steps on the host cores (OpenMP C port, oracle/d3m_oracle.c; oracle/_ref absent)" % steps
     tsdf_fps, _ = cpu_baseline_tsdf(3)
-    samples = sum(l["coords"].shape[0] for l in levels) * synth.N_VIEWS
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": min(args.warmup, 2), "ms_per_step": sec * 1e3, "higher_is_better": True,
+        "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "levels_N": [int(l["coords"].shape[0]) for l in levels], "views": synth.N_VIEWS,
-                   "samples_per_step": int(samples)},
-        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": "port",
-                         "sample": "%d full steps of the same 3-level fragment on the host cores (OpenMP C port of the "
-                                   "reference algorithm, oracle/d3m_oracle.c)" % steps},
+        "config": fragment_config(levels),
+        "cpu_baseline": {"value": v, "unit": "samples/s", "cores": cores, "kind": kind, "sample": sample,
+                         "port": {"value": port_v, "unit": "samples/s", "cores": port_cores, "ms_per_step": port_sec * 1e3}},
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "tsdf": {"frames_per_s": tsdf_fps, "unit": "frames/s", "volume": "512^3 @ 4 cm", "sample": "3 frames, C port"},
+        "tsdf": {"frames_per_s": tsdf_fps, "unit": "frames/s", "volume": "512^3 @ 4 cm", "kind": "port",
+                 "sample": "3 frames, OpenMP C port of the reference kernel (the reference's numpy CPU path needs ~20 GB "
+                           "and ~15 s per frame at 512^3)"},
         "gpu_launches": 0,
     }
     emit_json(line)
+
+
+# --------------------------------------------------------------------------------------------------
+# the reference's GPU path on this B200 (SURVEY §8d timing protocol)
+# --------------------------------------------------------------------------------------------------
+def bench_reference_gpu(torch, dev, levels, flush_buf, steps, our_ms_step, our_dense_ms):
+    """The UNMODIFIED reference back_project.py on CUDA (aten ops, forward + autograd backward), timed like our arm:
+    CUDA events, L2 flushed between steps, the same 3-level fragment and the dense level-2 call."""
+    from oracle import ref_gpu
+    if not ref_gpu.have_back_project():
+        return {"unavailable": "oracle/_ref/back_project.py not staged (built where /root/reference is mounted)"}
+    bp = ref_gpu.back_project_fn()
+    res = {}
+    tl = torch_levels(levels, dev)
+
+    def timed(fn, n):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(n):
+            flush_buf.fill_(1)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        return float(np.mean(ts)), float(min(ts))
+
+    samples = sum(l["coords"].shape[0] for l in levels) * synth.N_VIEWS
+    ms, ms_min = timed(lambda: reference_step(tl, bp), max(5, steps))
+    res["fragment"] = {"ms_per_step": ms, "ms_per_step_best": ms_min, "samples_per_s": samples / (ms * 1e-3),
+                       "ours_ms_per_step": our_ms_step, "speedup_ours": ms / our_ms_step if our_ms_step else None}
+    del tl
+    inp = synth.fragment_level_inputs(2)
+    inp["grad_out"] = synth.grad_out_for(inp["coords"].shape[0], synth.LEVELS[2]["C"])
+    dl = torch_levels([inp], dev)
+    ms, ms_min = timed(lambda: reference_step(dl, bp), 5)
+    N = inp["coords"].shape[0]
+    res["dense_level2"] = {"ms_fwd_bwd": ms, "ms_fwd_bwd_best": ms_min, "samples_per_s": N * synth.N_VIEWS / (ms * 1e-3),
+                           "ours_ms_fwd_bwd": our_dense_ms, "speedup_ours": ms / our_dense_ms if our_dense_ms else None}
+    res["what"] = ("oracle/_ref/back_project.py = byte-for-byte copy of the reference file, run unmodified on this GPU "
+                   "(torch %s aten kernels; backward = autograd, atomicAdd scatter)" % torch.__version__)
+    del dl
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_reference_gpu_tsdf(torch, dev, n_frames=60):
+    """The reference's PyCUDA kernel string compiled verbatim (oracle/_ref/libref_tsdf.so) with the reference launch
+    geometry, one launch over all 512^3 voxels per frame, plus the per-call copies pycuda's InOut does for the depth
+    frame (host -> device before the launch, device -> host after it, pageable numpy memory)."""
+    from oracle import ref_gpu
+    if not ref_gpu.have_tsdf():
+        return {"unavailable": "oracle/_ref/libref_tsdf.so not built"}
+    L = ref_gpu.tsdf_lib()
+    dims = (512, 512, 512)
+    tsdf = torch.ones(dims, dtype=torch.float32, device=dev)
+    weight = torch.zeros(dims, dtype=torch.float32, device=dev)
+    color = torch.zeros(dims, dtype=torch.float32, device=dev)
+    origin = np.zeros(3, np.float32)
+    K = np.ascontiguousarray(synth.tsdf_intrinsics().astype(np.float32).reshape(-1))
+    dimg = torch.empty((480, 640), dtype=torch.float32, device=dev)
+    cimg = torch.zeros((1,), dtype=torch.float32, device=dev)
+    frames = [(np.ascontiguousarray(synth.tsdf_depth(f)), np.ascontiguousarray(synth.tsdf_pose(f).astype(np.float32).reshape(-1)))
+              for f in range(n_frames + 2)]
+
+    def one(depth, pose):
+        dimg.copy_(torch.from_numpy(depth))              # InOut: host -> device
+        rc = L.ref_tsdf_integrate(tsdf.data_ptr(), weight.data_ptr(), color.data_ptr(), 512, 512, 512,
+                                  origin.ctypes.data, K.ctypes.data, pose.ctypes.data, 0.04, 480, 640, 0.12, 1.0,
+                                  cimg.data_ptr(), dimg.data_ptr(), None)
+        assert rc == 0, "ref_tsdf_integrate failed: %d" % rc
+        depth[...] = dimg.cpu().numpy()                  # InOut: device -> host
+
+    for d, p in frames[:2]:
+        one(d, p)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for d, p in frames[2:]:
+        one(d, p)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    # kernel-only: frames resident, no copies
+    d_res = torch.from_numpy(frames[2][0]).to(dev)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _, p in frames[2:12]:
+        L.ref_tsdf_integrate(tsdf.data_ptr(), weight.data_ptr(), color.data_ptr(), 512, 512, 512, origin.ctypes.data,
+                             K.ctypes.data, p.ctypes.data, 0.04, 480, 640, 0.12, 1.0, cimg.data_ptr(), d_res.data_ptr(), None)
+    torch.cuda.synchronize()
+    dk = (time.perf_counter() - t0) / 10
+    del tsdf, weight, color
+    torch.cuda.empty_cache()
+    return {"frames_per_s": n_frames / dt, "ms_per_frame": dt / n_frames * 1e3, "ms_per_frame_launch_only": dk * 1e3,
+            "frames": n_frames, "volume": "512^3 @ 4 cm",
+            "what": "verbatim reference CUDA kernel (tsdf_volume.py:68-142), reference launch geometry (:147-155), per-call "
+                    "depth H2D + D2H as pycuda InOut (:232-256)"}
+
+
+def kernel_touched_bytes(kernel, N, S, V, B, C, H, W, cb):
+    """Bytes ONE launch of `kernel` itself loads + stores (each access counted once at its granularity)."""
+    maps = 4 * V * B * C * H * W
+    rows_out = N * (4 * (C + 1) + 4)
+    if kernel == "bp_fwd":      # coords in, 4 corner texels per valid sample, rows + count (+ zbar/bidx, records) out
+        return N * cb + 16 * C * S + rows_out + 8 * N + 64 * V * B
+    if kernel == "bp_bwd_gather":   # cell-centric: every ghat row read ONCE per sample, entry 16 B, maps written once
+        return 4 * C * S + 16 * S + maps + 8 * V * B * H * W
+    if kernel in ("relayout_transpose", "bp_prep"):
+        return 2 * maps
+    if kernel in ("bp_bwd_fill", "bp_bwd_fill_ghat"):
+        return N * cb + 16 * S + 8 * S + (N * (8 * C + 8) if kernel.endswith("ghat") else 0)
+    if kernel == "bp_bwd_order":
+        return 32 * S + 8 * S
+    if kernel == "bp_bwd_scan_ghat":
+        return 12 * V * B * H * W + N * (8 * C + 8)
+    if kernel in ("bp_fwd_normalise", "bp_fwd_finish"):
+        return 12 * N + (12 * V * B * H * W if kernel == "bp_fwd_finish" else 0)
+    if kernel == "bp_fwd_stats":
+        return 8 * N
+    return 0
 
 
 # --------------------------------------------------------------------------------------------------
@@ -431,10 +620,24 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         dense = bench_dense_l2(torch, dev, _lib, back_project, flush_buf, peak_gbs, args.steps)
 
-    # ---- TSDF leg (rank 0 only; replicas only across ranks) -------------------------------------------
+    # ---- the reference's own GPU path on this B200 (rank 0, N=1 only: SURVEY §8d timing protocol) ------------
+    ref_gpu_res = None
+    if rank == 0 and world == 1 and not args.no_reference_gpu:
+        try:
+            ref_gpu_res = {"back_project": bench_reference_gpu(torch, dev, levels, flush_buf, args.steps, ms_step,
+                                                               dense["ms_fwd_bwd"] if dense else None),
+                           "tsdf": bench_reference_gpu_tsdf(torch, dev)}
+        except Exception as err:  # a baseline leg never takes the headline line down
+            log("reference_gpu leg failed:", repr(err))
+            ref_gpu_res = {"error": repr(err)[:300]}
+
+    # ---- TSDF leg: config 3 on rank 0 (replicas only), then the x-slab sharded volume on every rank -----------
     tsdf = None
     if rank == 0:
         tsdf = bench_tsdf(torch, dev, _lib, TSDFVolume, peak_gbs, flush_buf, with_cpu=(world == 1))
+    tsdf_slabs = bench_tsdf_slabs(torch, dist, dev, TSDFVolume, flush_buf, rank, world)
+    if tsdf is not None:
+        tsdf["x_slabs"] = tsdf_slabs
 
     # ---- SURVEY §8 rows f2 / f3 (rank 0 only): level glue around back_project, GRU-fusion volume movement ----
     glue = fus = gtt = dgen = None
@@ -470,61 +673,62 @@ def run_ours(args, rank, world, local_rank):
 
     value = total_samples / (ms_step * 1e-3)
     e2e_value = total_samples / (ms_e2e * 1e-3)
-    # dominant kernel over the whole step and its roofline
+    # ---- roofline.  The lead figure is the WHOLE STEP: algorithmic bytes of the three forward + backward
+    # passes over the timed step.  Per pass the same formula over the pass's kernels; per kernel the bytes that kernel
+    # itself moves ("touched": every load/store it issues counted once at its granularity), never a share of A_bwd.
     tot_ms = {}
     for acc in prof:
         for k, v in acc.items():
             tot_ms[k] = tot_ms.get(k, 0.0) + v["ms"]
     kern_total = sum(tot_ms.values())
     dom = max(tot_ms, key=tot_ms.get)
-    # dominant (kernel, level) pair: algorithmic bytes are per level
     best = None
     for li, acc in enumerate(prof):
-        if dom in acc:
-            a_fwd, a_bwd = algorithmic_bytes(levels[li], S_levels[li])
-            ms = acc[dom]["ms"] / max(1, acc[dom]["n"])
-            if best is None or acc[dom]["ms"] > best[0]:
-                best = (acc[dom]["ms"], li, ms, a_fwd, a_bwd)
-    _, li, ms_k, a_fwd, a_bwd = best
+        if dom in acc and (best is None or acc[dom]["ms"] > best[0]):
+            best = (acc[dom]["ms"], li, acc[dom]["ms"] / max(1, acc[dom]["n"]))
+    _, li, ms_k = best
     V, B, C, H, W = levels[li]["feats"].shape
-    if dom == "bp_fwd":
-        alg = a_fwd
-    elif dom == "bp_bwd_gather":
-        alg = 16 * C * S_levels[li] + 4 * V * B * C * H * W + 16 * S_levels[li]
-    else:
-        alg = a_bwd
-    achieved = alg / (ms_k * 1e-3) / 1e9
-    # compulsory variant: every byte once -- the gather term 16*C*S replaced by one pass over the maps
-    N_dom = int(levels[li]["coords"].shape[0])
+    N_dom, S_dom = int(levels[li]["coords"].shape[0]), S_levels[li]
     cb = levels[li]["coords"].dtype.itemsize * 4
-    row_io = N_dom * (cb + 4 * (C + 1) + 4)
-    if dom == "bp_fwd":
-        compulsory = row_io + 4 * V * B * C * H * W + 64 * V * B
-    elif dom == "bp_bwd_gather":
-        compulsory = 4 * N_dom * C + 16 * S_levels[li] + 4 * V * B * C * H * W
-    else:
-        compulsory = row_io + 4 * V * B * C * H * W
+    touched = kernel_touched_bytes(dom, N_dom, S_dom, V, B, C, H, W, cb)
     traffic, traffic_src = ncu_traffic(dom, li)
-    a_path = sum(sum(algorithmic_bytes(l, s)) for l, s in zip(levels, S_levels))
+    a_path = sum(sum(algorithmic_bytes(l, s_)) for l, s_ in zip(levels, S_levels))
     path_gbs = a_path / (ms_step * 1e-3) / 1e9
+    FWD_K = ("relayout_transpose", "bp_prep", "zero_words", "bp_fwd", "bp_fwd_stats", "bp_fwd_normalise", "bp_fwd_finish")
+    per_pass = []
+    for lv, (acc, l, s_) in enumerate(zip(prof, levels, S_levels)):
+        a_f, a_b = algorithmic_bytes(l, s_)
+        f_ms = sum(v["ms"] for k, v in acc.items() if k in FWD_K) / args.steps
+        b_ms = sum(v["ms"] for k, v in acc.items() if k not in FWD_K) / args.steps
+        per_pass.append({"level": lv, "fwd_GBs": a_f / (f_ms * 1e-3) / 1e9 if f_ms else None,
+                         "bwd_GBs": a_b / (b_ms * 1e-3) / 1e9 if b_ms else None,
+                         "fwd_frac": a_f / (f_ms * 1e-3) / 1e9 / peak_gbs if f_ms else None,
+                         "bwd_frac": a_b / (b_ms * 1e-3) / 1e9 / peak_gbs if b_ms else None,
+                         "fwd_kernels_ms": f_ms, "bwd_kernels_ms": b_ms})
     cpu_base = None
     if world == 1:  # reported on rank 0 at N=1 only (the ranks of a multi-GPU run share the host cores)
-        cpu_v, cpu_sec, cores = cpu_baseline_bp(levels, 5, 1)
-        cpu_base = {"value": cpu_v, "unit": "samples/s", "cores": cores, "kind": "port",
-                    "sample": "5 full steps of the same fragment on the host (OpenMP C port of the reference "
-                              "algorithm; %.1f ms/step)" % (cpu_sec * 1e3)}
+        port_v, port_sec, port_cores = cpu_baseline_bp(levels, 5, 1)
+        ref = None if args.no_reference_cpu else cpu_reference_bp(levels, 5, 1)
+        if ref is not None:
+            cpu_base = {"value": ref[0], "unit": "samples/s", "cores": ref[2], "kind": "reference",
+                        "sample": "5 full steps of the same fragment through the unmodified reference back_project.py on "
+                                  "the host (torch CPU ops + autograd; %.0f ms/step)" % (ref[1] * 1e3),
+                        "port": {"value": port_v, "unit": "samples/s", "cores": port_cores, "ms_per_step": port_sec * 1e3,
+                                 "what": "OpenMP C restatement of the same algorithm (oracle/d3m_oracle.c)"}}
+        else:
+            cpu_base = {"value": port_v, "unit": "samples/s", "cores": port_cores, "kind": "port",
+                        "sample": "5 full steps of the same fragment on the host (OpenMP C port of the reference "
+                                  "algorithm; %.1f ms/step)" % (port_sec * 1e3)}
+    cfg = fragment_config(levels)
     line = {
         "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "levels_N": [int(l["coords"].shape[0]) for l in levels],
-                   "levels_valid_samples": S_levels, "views": synth.N_VIEWS, "channels": [80, 40, 24],
-                   "coords_dtype": ["float32", "int64", "int64"], "samples_per_step": int(samples),
-                   "fragments_per_gpu": 1, "parallelism": "fragment-parallel x%d (no data-path collective)" % world,
-                   "l2": "256 MiB buffer written between timed steps (L2 flush); per-step CUDA events"},
+        "config": cfg, "levels_valid_samples": S_levels,
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "ms_per_step": ms_e2e, "what": "back_project() public API from pinned host tensors; volume, count and "
+                "ms_per_step": ms_e2e, "h2d_GBs_per_rank": h2d / (ms_e2e * 1e-3) / 1e9, "d2h_GBs_per_rank": d2h / (ms_e2e * 1e-3) / 1e9,
+                "what": "back_project() public API from pinned host tensors; volume, count and "
                 "grad_feats copied back to pinned host memory every step; one CUDA stream per level, forward phase of all "
                 "levels issued before the backward phase, so that H2D, kernels and D2H overlap (PCIe-bound: the step "
                 "moves 51 MB in and 47 MB out)"},
@@ -533,24 +737,28 @@ def run_ours(args, rank, world, local_rank):
         "kernel_chaining": ("programmatic dependent launch (griddepcontrol)" if os.environ.get("D3M_PDL", "1") != "0"
                             else "plain stream serialisation (D3M_PDL=0)"),
         "ms_per_step_graph": ms_graph, "graph_error": graph_err,
-        "roofline": {"bound": "hbm", "kernel": dom, "level": li, "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": achieved / peak_gbs, "traffic": traffic, "traffic_source": traffic_src,
-                     "peak_source": peak_src,
-                     "algorithmic_bytes_per_launch": int(alg), "ms_per_launch": ms_k,
-                     "kernel_share_of_step": tot_ms[dom] / kern_total,
-                     "served_by": "L2" if (traffic is not None and traffic < 0.5 * alg) else "HBM",
-                     "compulsory": {"bytes_per_launch": int(compulsory), "achieved": compulsory / (ms_k * 1e-3) / 1e9,
-                                    "frac": compulsory / (ms_k * 1e-3) / 1e9 / peak_gbs,
-                                    "what": "every byte once: rows in/out + one pass over the feature maps"},
-                     "note": "L2-served: the feature maps are L2-resident at fragment size (SURVEY §8d), so `achieved` counts "
-                             "the 4 corner texels of every valid sample (bytes a cache-less machine would move) and may "
-                             "exceed the HBM peak; `traffic` is the measured DRAM traffic, `compulsory` the every-byte-once "
-                             "figure"},
-        "path_roofline": {"algorithmic_bytes_per_step": int(a_path), "achieved": path_gbs, "frac": path_gbs / peak_gbs,
-                          "frac_of_nominal_8TBs": path_gbs / 8000.0},
+        "roofline": {"bound": "hbm", "kernel": "whole step: back_project fwd+bwd x 3 levels (every kernel of the path)",
+                     "achieved": path_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": path_gbs / peak_gbs,
+                     "frac_of_nominal_8TBs": path_gbs / 8000.0, "peak_source": peak_src,
+                     "algorithmic_bytes_per_step": int(a_path), "ms_per_step": ms_step,
+                     "traffic": traffic, "traffic_source": traffic_src,
+                     "formula": "SURVEY 8(d): sum over levels of A_fwd + A_bwd, divided by the timed step (graph replay, L2 "
+                                "flushed); 16*C*S counts the 4 corner texels of every valid sample, which the L2-resident maps "
+                                "serve -- DRAM traffic is far lower (see dominant_kernel.traffic)",
+                     "per_pass": per_pass,
+                     "dominant_kernel": {"kernel": dom, "level": li, "ms_per_launch": ms_k,
+                                         "touched_bytes_per_launch": int(touched),
+                                         "touched_GBs": touched / (ms_k * 1e-3) / 1e9,
+                                         "touched_frac_of_peak": touched / (ms_k * 1e-3) / 1e9 / peak_gbs,
+                                         "dram_traffic_per_launch": traffic, "dram_traffic_source": traffic_src,
+                                         "share_of_profile_pass": tot_ms[dom] / kern_total,
+                                         "note": "share of the per-kernel event-timed profile pass (events serialise the "
+                                                 "launches: their sum exceeds the PDL-overlapped timed step)"}},
         "kernel_ms_per_step": {k: v / args.steps for k, v in sorted(tot_ms.items())},
         "kernel_us_per_level": [{k: round(1e3 * v["ms"] / args.steps, 2) for k, v in sorted(acc.items())} for acc in prof],
+        "launches_per_level": [int(sum(v["n"] for v in acc.values()) / args.steps) for acc in prof],
         "cpu_baseline": cpu_base,
+        "reference_gpu": ref_gpu_res,
         "dense_level2": dense,
         "batched_fragments": batched,
         "large_scene": scene,
@@ -559,6 +767,14 @@ def run_ours(args, rank, world, local_rank):
         "gru_fusion": fus,
         "gt_transform": gtt,
         "datagen": dgen,
+        # last on purpose: the driver keeps the tail of the line
+        "strong_scaling": {"n_gpus": world,
+                           "batched_64frag_ms": round(batched["ms_per_step"], 4) if batched else None,
+                           "large_scene_ms": round(scene["ms_per_step"], 4) if scene else None,
+                           "large_scene_parity": scene.get("parity") if scene else None,
+                           "tsdf_slabs_300f_ms": round(tsdf_slabs["ms_batch_300"], 4) if tsdf_slabs else None,
+                           "tsdf_slabs_bit_equal": tsdf_slabs.get("bit_equal_to_unsharded") if tsdf_slabs else None,
+                           "e2e_ms": round(ms_e2e, 4), "value_ms": round(ms_step, 5)},
     }
     emit_json(line)
     if world > 1:
@@ -648,9 +864,12 @@ def bench_batched_fragments(torch, dist, dev, back_project, levels, flush_buf, r
 def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     """BASELINE configs[4]: 1024^3 index space @ 4 cm, 64 views, finest level (C=24, 120x160 maps), wall-shell sparse set
     (~1 % occupancy), voxel-range sharded (block-cyclic ranges): feats / KRcam replicated, each rank gathers its slice; per step
-    one all-reduce of 3 fp64 scalars (depth normalisation), one all-reduce of grad_feats (118 MB) and one all-gather of
-    the per-shard view counts (the occupancy slab the next coarse-to-fine level needs)."""
-    from deep3dmap_b200 import shard
+    one all-reduce of 3 fp64 scalars (depth normalisation), one exchange of grad_feats (118 MB) and one all-gather of
+    the per-shard view counts (the occupancy slab the next coarse-to-fine level needs).
+    EVERY run with more than one rank also proves parity of the multi-rank path on the real shape: the all-gathered count
+    must equal the unsharded count computed on rank 0 bit for bit, and the exchanged grad_feats must match the unsharded
+    gradient to the 1e-5 bar (norm-wise, as in tests/test_gpu_back_project.py::test_large_scene_config5_real_shape)."""
+    from deep3dmap_b200 import back_project, shard
     V, lv = 64, 2
     L = synth.LEVELS[lv]
     coords_all = synth.large_scene_coords(dtype=np.int32)
@@ -660,15 +879,15 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     coords = torch.from_numpy(np.ascontiguousarray(coords_all[mine.numpy()])).to(dev)
     n_local = int(mine.numel())
     inv_perm = shard.blocks_inverse_permutation(N, world).to(dev) if world > 1 else None
-    del coords_all
     R, c = synth.large_scene_cameras(V)
     KR = torch.from_numpy(synth.krcam_from(R, c, synth.scaled_K(L["scale"]))[:, None].copy()).to(dev)
     origin = torch.zeros((1, 3), device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(777)  # same seed on every rank: replicated feature maps
     feats = torch.randn((V, 1, L["C"], L["H"], L["W"]), device=dev, generator=gen).requires_grad_(True)
-    gen.manual_seed(778 + rank)
-    go = torch.randn((n_local, L["C"] + 1), device=dev, generator=gen)
+    gen.manual_seed(778)  # same seed on every rank: grad_out of the whole scene, each rank keeps the rows of its voxels
+    go_all = torch.randn((N, L["C"] + 1), device=dev, generator=gen)
+    go = go_all[mine.to(dev)].contiguous() if world > 1 else go_all
     sizes = [int(shard.voxel_blocks(N, r, world).numel()) for r in range(world)]
 
     def step():
@@ -681,11 +900,36 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     for _ in range(2):
         full_cnt, cnt = step()
     torch.cuda.synchronize()
-    S = torch.tensor([float(cnt.sum().item())], device=dev, dtype=torch.float64)
+    # ---- parity of the multi-rank path, on the real shape, every run ----------------------------------------------
+    parity = {"checked": False, "why": "single rank: sharded == unsharded by construction"}
+    if world > 1:
+        ok = torch.ones(1, device=dev)
+        if rank == 0:
+            f_ref = feats.detach().clone().requires_grad_(True)
+            v_ref, c_ref = back_project(torch.from_numpy(coords_all).to(dev), origin, synth.VOXEL_SIZE, f_ref, KR)
+            v_ref.backward(go_all)
+            count_equal = bool(torch.equal(full_cnt, c_ref))
+            err = (feats.grad.double() - f_ref.grad.double())
+            ref_l2 = float(f_ref.grad.double().norm())
+            ref_max = float(f_ref.grad.abs().max())
+            rel_l2 = float(err.norm()) / max(ref_l2, 1e-30)
+            rel_max = float(err.abs().max()) / max(ref_max, 1e-30)
+            parity = {"checked": True, "count_bit_equal": count_equal, "grad_rel_l2": rel_l2, "grad_max_err_over_max": rel_max,
+                      "bars": {"grad_rel_l2": 1e-6, "grad_max_err_over_max": 1e-5},
+                      "pass": bool(count_equal and rel_l2 <= 1e-6 and rel_max <= 1e-5),
+                      "against": "unsharded back_project of all %d voxels on rank 0 (same feats / grad_out)" % N}
+            ok[0] = 1.0 if parity["pass"] else 0.0
+            del f_ref, v_ref, c_ref, err
+        dist.broadcast(ok, 0)
+        if float(ok[0]) != 1.0:
+            raise AssertionError("large-scene multi-rank parity FAILED: %r" % (parity,))
+    del coords_all, go_all
+    torch.cuda.empty_cache()
+    S = torch.tensor([float(cnt.double().sum().item())], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(S)
     ts = []
-    for _ in range(3):
+    for _ in range(5):
         flush_buf.fill_(1)
         if world > 1:
             dist.barrier()
@@ -702,10 +946,60 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     kern = {k: round(v["ms"], 3) for k, v in sorted(_lib.profile_end().items())}
     res = {"kernel_ms_rank0": kern, "index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": n_local, "partition": "block-cyclic voxel ranges (4096 voxels per block)",
            "samples_per_step": int(N) * V, "valid_samples": int(S[0].item()), "ms_per_step": ms,
-           "samples_per_s": N * V / (ms * 1e-3), "scaling": "strong",
-           "collectives": "all_reduce(3 fp64 per fragment) + all_reduce(grad_feats %.0f MB) + all_gather(count, %d B/voxel)"
-                          % (feats.numel() * 4 / 1e6, 4), "full_count_rows": int(full_cnt.shape[0])}
+           "samples_per_s": N * V / (ms * 1e-3), "scaling": "strong", "parity": parity,
+           "collectives": "all_reduce(3 fp64 per fragment) + %s(grad_feats %.0f MB) + all_gather(count, %d B/voxel)"
+                          % (shard.grad_exchange_name(), feats.numel() * 4 / 1e6, 4), "full_count_rows": int(full_cnt.shape[0])}
     del coords, feats, go
+    torch.cuda.empty_cache()
+    return res
+
+
+def bench_tsdf_slabs(torch, dist, dev, TSDFVolume, flush_buf, rank, world):
+    """SURVEY 8(e) row 3 on real GPUs: the 512^3 volume of config 3 cut into x slabs, one per rank (zero exchange while
+    integrating; every rank reads every frame), 300 resident frames in one launch per rank, timed as the max over ranks.
+    The reassembled volume (`shard.gather_tsdf_volume`, NCCL all-gather of the slabs) is compared bit for bit with the
+    unsharded volume that rank 0 integrates from the same frames -- in every run."""
+    from deep3dmap_b200 import shard
+    F = N_TSDF_FRAMES
+    K = synth.tsdf_intrinsics()
+    poses = np.stack([synth.tsdf_pose(f) for f in range(F)])
+    d_dev = torch.from_numpy(np.stack([synth.tsdf_depth(f) for f in range(F)])).to(dev)
+    bnds = np.array([[0.0, 20.48]] * 3)
+    slab = shard.tsdf_slab(512, rank, world)
+    vol = TSDFVolume(bnds.copy(), 0.04, margin=3, slab=slab if world > 1 else None)
+    vol.integrate_batch(d_dev, K, poses)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(5):
+        vol.reset()
+        flush_buf.fill_(1)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); vol.integrate_batch(d_dev, K, poses); b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = _max_over_ranks(torch, dist, dev, float(min(ts)), world)
+    res = {"ranks": world, "slab_planes_rank0": int(slab[1] - slab[0]), "ms_batch_300": ms, "frames_per_s": F / (ms * 1e-3),
+           "exchange_while_integrating": "none", "bit_equal_to_unsharded": None}
+    if world > 1:
+        lt, lw, _ = vol.device_volumes()
+        ft, fw = shard.gather_tsdf_volume(torch.as_tensor(lt, device=dev), torch.as_tensor(lw, device=dev), 512)
+        ok = torch.ones(1, device=dev)
+        if rank == 0:
+            full = TSDFVolume(bnds.copy(), 0.04, margin=3)
+            full.integrate_batch(d_dev, K, poses)
+            rt, rw, _ = full.device_volumes()
+            eq = bool(torch.equal(ft, torch.as_tensor(rt, device=dev)) and torch.equal(fw, torch.as_tensor(rw, device=dev)))
+            ok[0] = 1.0 if eq else 0.0
+            del full
+        dist.broadcast(ok, 0)
+        res["bit_equal_to_unsharded"] = bool(float(ok[0]) == 1.0)
+        if not res["bit_equal_to_unsharded"]:
+            raise AssertionError("TSDF x-slab volume differs from the unsharded volume")
+        del ft, fw
+    del vol, d_dev
     torch.cuda.empty_cache()
     return res
 
@@ -1259,6 +1553,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time the eager python path only")
+    ap.add_argument("--no-reference-gpu", action="store_true", help="skip the reference-on-this-GPU legs")
+    ap.add_argument("--no-reference-cpu", action="store_true", help="cpu_baseline from the C port only (skips ~5 s of torch CPU)")
     ap.add_argument("--legs", default="all", choices=["all", "glue", "datagen"], help="'glue': only the level-glue / GRU-fusion legs")
     ap.add_argument("--profile-step", default="", choices=["", "bp", "tsdf", "dense"],
                     help="profiler target: run only the hot-path steps (and the TSDF launches with 'tsdf'), print nothing")

@@ -11,13 +11,13 @@ LIB_PATH = os.path.join(_HERE, "libd3m.so")
 
 # every symbol include/d3m.h declares
 SYMBOLS = (
-    "d3m_version", "d3m_last_error", "d3m_device_count",
+    "d3m_version", "d3m_last_error", "d3m_device_count", "d3m_current_device",
     "d3m_kernel_launches", "d3m_profile_begin", "d3m_profile_end",
     "d3m_feats_nchw_to_nhwc", "d3m_feats_nhwc_to_nchw",
     "d3m_back_project_fwd_workspace", "d3m_back_project_cell_hist_elems", "d3m_back_project_fwd",
     "d3m_back_project_fwd_partial", "d3m_back_project_fwd_finish",
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
-    "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_reset", "d3m_tsdf_rebase", "d3m_tsdf_integrate_host",
+    "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_device", "d3m_tsdf_reset", "d3m_tsdf_rebase", "d3m_tsdf_integrate_host",
     "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches", "d3m_upload",
     # ground-truth side of the dataloader transform
     "d3m_tsdf_occupancy", "d3m_gt_recrop",
@@ -53,6 +53,7 @@ def lib():
     L.d3m_version.restype = i32
     L.d3m_last_error.restype = ctypes.c_char_p
     L.d3m_device_count.restype = i32
+    L.d3m_current_device.restype = i32
     L.d3m_kernel_launches.restype = i64
     L.d3m_profile_begin.restype = i32
     L.d3m_profile_end.argtypes = [ctypes.c_char_p, sz]
@@ -81,6 +82,8 @@ def lib():
     L.d3m_tsdf_create_slab.restype = i32
     L.d3m_tsdf_destroy.argtypes = [vp]
     L.d3m_tsdf_destroy.restype = i32
+    L.d3m_tsdf_device.argtypes = [vp]
+    L.d3m_tsdf_device.restype = i32
     L.d3m_tsdf_reset.argtypes = [vp, vp]
     L.d3m_tsdf_reset.restype = i32
     L.d3m_tsdf_rebase.argtypes = [vp, vp, f32, f32, vp]

@@ -138,6 +138,15 @@ extern "C" int d3m_device_count(void) {
   return n;
 }
 
+extern "C" int d3m_current_device(void) {
+  int d = -1;
+  if (d3m_device_count() <= 0 || cudaGetDevice(&d) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
+  }
+  return d;
+}
+
 extern "C" int64_t d3m_kernel_launches(void) { return (int64_t)d3m::g_launches.load(); }
 
 extern "C" int d3m_profile_begin(void) {

@@ -37,6 +37,25 @@ struct LaunchScope {
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: handle-owning entry
+// points (d3m_tsdf_*) must not leave the calling thread on another GPU (torch allocations would silently follow).
+struct DeviceGuard {
+  explicit DeviceGuard(int device) : prev_(-1), switched_(false), err_(cudaSuccess) {
+    err_ = cudaGetDevice(&prev_);
+    if (err_ == cudaSuccess && prev_ != device) {
+      err_ = cudaSetDevice(device);
+      switched_ = (err_ == cudaSuccess);
+    }
+  }
+  ~DeviceGuard() {
+    if (switched_) cudaSetDevice(prev_);
+  }
+  cudaError_t error() const { return err_; }
+  int prev_;
+  bool switched_;
+  cudaError_t err_;
+};
+
 // ------------------------------------------------------------------------------------------------
 // Programmatic dependent launch (griddepcontrol, sm_90+).  The fragment-sized step is a chain of 5-45 us kernels, so
 // the launch ramp of kernel K+1 (CTA dispatch, parameter and instruction fetch) is a visible share of the step.  Every
@@ -150,11 +169,20 @@ __device__ __forceinline__ Sample project(float gx, float gy, float gz, const fl
   const float p0 = __fadd_rn(__fmaf_rn(r0.z, gz, __fmaf_rn(r0.y, gy, __fmul_rn(r0.x, gx))), r0.w);
   const float p1 = __fadd_rn(__fmaf_rn(r1.z, gz, __fmaf_rn(r1.y, gy, __fmul_rn(r1.x, gx))), r1.w);
   const float p2 = __fadd_rn(__fmaf_rn(r2.z, gz, __fmaf_rn(r2.y, gy, __fmul_rn(r2.x, gx))), r2.w);
+  // Early outs before the four IEEE divisions (most samples of a large scene are far outside the image).  Both are
+  // exact with respect to the test below: `valid` needs p2 > 0; and for p2 > 0 a pixel coordinate more than 0.1 % of the
+  // image size outside [0, W-1] x [0, H-1] cannot round back inside (the rounding error of the chain is ~1e-6 relative).
+  // Borderline samples fall through to the reference arithmetic, so count / masks stay bit-exact.
+  s.z = p2; s.fx = 0.0f; s.fy = 0.0f; s.x0 = 0; s.y0 = 0; s.valid = false;
+  if (!(p2 > 0.0f)) return s;
+  {
+    const float mx = __fmul_rn(1e-3f, wm1), my = __fmul_rn(1e-3f, hm1);
+    if (p0 < -mx * p2 || p0 > (wm1 + mx) * p2 || p1 < -my * p2 || p1 > (hm1 + my) * p2) return s;
+  }
   const float u = __fdiv_rn(p0, p2);
   const float v = __fdiv_rn(p1, p2);
   const float nx = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, u), wm1), 1.0f);
   const float ny = __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, v), hm1), 1.0f);
-  s.z = p2;
   s.valid = (fabsf(nx) <= 1.0f) && (fabsf(ny) <= 1.0f) && (p2 > 0.0f);
   const float ix = __fmul_rn(__fmul_rn(__fadd_rn(nx, 1.0f), 0.5f), wm1);
   const float iy = __fmul_rn(__fmul_rn(__fadd_rn(ny, 1.0f), 0.5f), hm1);

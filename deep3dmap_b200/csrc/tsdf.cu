@@ -571,7 +571,8 @@ extern "C" int d3m_tsdf_create_slab(int dim_x, int dim_y, int dim_z, int x_begin
   D3M_REQUIRE(dim_x > 0 && dim_y > 0 && dim_z > 0 && x_begin >= 0 && origin3_host && voxel_size > 0.f &&
                   trunc_margin > 0.f,
               D3M_ERR_ARG, "tsdf_create: bad arguments");
-  D3M_CUDA_CHECK(cudaSetDevice(device));
+  DeviceGuard dev_guard(device);
+  D3M_CUDA_CHECK(dev_guard.error());
   d3m_tsdf* h = new (std::nothrow) d3m_tsdf();
   D3M_REQUIRE(h, D3M_ERR_ARG, "tsdf_create: out of host memory");
   memset(h, 0, sizeof(*h));
@@ -598,7 +599,7 @@ extern "C" int d3m_tsdf_create_slab(int dim_x, int dim_y, int dim_z, int x_begin
 
 extern "C" int d3m_tsdf_destroy(d3m_tsdf* h) {
   if (!h) return D3M_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard dev_guard(h->device);
   cudaDeviceSynchronize();
   cudaFree(h->tsdf); cudaFree(h->weight); cudaFree(h->color);
   for (int i = 0; i < kRing; ++i) {
@@ -616,7 +617,8 @@ extern "C" int d3m_tsdf_destroy(d3m_tsdf* h) {
 extern "C" int d3m_tsdf_reset(d3m_tsdf* h, void* stream_) {
   D3M_REQUIRE(h, D3M_ERR_ARG, "tsdf_reset: NULL handle");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  D3M_CUDA_CHECK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
+  D3M_CUDA_CHECK(dev_guard.error());
   {
     LaunchScope ls("tsdf_fill", stream);
     fill_kernel<<<h->sms * 8, 256, 0, stream>>>(h->tsdf, 1.0f, (int64_t)h->nvox);
@@ -664,7 +666,8 @@ extern "C" int d3m_tsdf_integrate_device(d3m_tsdf* h, const float* depth, const 
   D3M_REQUIRE(h && depth && intr9_host && pose16_host && n_frames >= 0 && H > 0 && W > 0, D3M_ERR_ARG,
               "tsdf_integrate: bad arguments");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  D3M_CUDA_CHECK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
+  D3M_CUDA_CHECK(dev_guard.error());
   h->last_launches = 0;
   for (int f0 = 0; f0 < n_frames; f0 += kMaxFramesPerLaunch) {
     const int F = (n_frames - f0) < kMaxFramesPerLaunch ? (n_frames - f0) : kMaxFramesPerLaunch;
@@ -686,7 +689,8 @@ extern "C" int d3m_tsdf_integrate_host(d3m_tsdf* h, const float* depth_host, con
   D3M_REQUIRE(h && depth_host && intr9_host && pose16_host && H > 0 && W > 0, D3M_ERR_ARG,
               "tsdf_integrate_host: bad arguments");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  D3M_CUDA_CHECK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
+  D3M_CUDA_CHECK(dev_guard.error());
   const size_t hw = (size_t)H * W;
   if (h->frame_cap < 2 * hw) {
     D3M_CUDA_CHECK(cudaDeviceSynchronize());
@@ -767,12 +771,15 @@ extern "C" int d3m_upload(const void* host_src, void* dev_dst, size_t bytes, voi
 extern "C" int d3m_tsdf_download(d3m_tsdf* h, float* tsdf_host, float* weight_host, float* color_host, void* stream_) {
   D3M_REQUIRE(h, D3M_ERR_ARG, "tsdf_download: NULL handle");
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  D3M_CUDA_CHECK(cudaSetDevice(h->device));
+  DeviceGuard dev_guard(h->device);
+  D3M_CUDA_CHECK(dev_guard.error());
   if (tsdf_host) D3M_CUDA_CHECK(cudaMemcpyAsync(tsdf_host, h->tsdf, h->nvox * 4, cudaMemcpyDeviceToHost, stream));
   if (weight_host) D3M_CUDA_CHECK(cudaMemcpyAsync(weight_host, h->weight, h->nvox * 4, cudaMemcpyDeviceToHost, stream));
   if (color_host) D3M_CUDA_CHECK(cudaMemcpyAsync(color_host, h->color, h->nvox * 4, cudaMemcpyDeviceToHost, stream));
   D3M_CUDA_CHECK(cudaStreamSynchronize(stream));
   return D3M_OK;
 }
+
+extern "C" int d3m_tsdf_device(d3m_tsdf* h) { return h ? h->device : -1; }
 
 extern "C" int d3m_tsdf_last_launches(d3m_tsdf* h) { return h ? h->last_launches : 0; }

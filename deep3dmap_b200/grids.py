@@ -212,6 +212,8 @@ def nonzero_ordered(flags, invert=False, values=None, sync=True):
     total = torch.empty((1,), dtype=torch.int64, device=dev)
     nbytes = _cmp_ws.get(N)
     if nbytes is None:
+        if len(_cmp_ws) >= 4096:   # N differs per fragment on the sparse levels: keep the memo bounded
+            _cmp_ws.clear()
         nbytes = _cmp_ws[N] = _lib.lib().d3m_compact_workspace(N)
     ws = torch.empty((max(nbytes, 8),), dtype=torch.uint8, device=dev)
     if values is not None:
@@ -245,9 +247,39 @@ def drop_ranks(ind, choice):
     return kept
 
 
+class _GatherRows(torch.autograd.Function):
+    """`src[ind]` with autograd to `src` for UNIQUE indices (what `nonzero_ordered` produces): the backward places the
+    incoming rows into zeros (index_put backward of gru_fusion.py:236) through the unique-owner scatter kernel."""
+
+    @staticmethod
+    def forward(ctx, src, ind):
+        ctx.save_for_backward(ind)
+        ctx.src_shape = tuple(src.shape)
+        return _gather_rows_raw(src.detach(), ind)
+
+    @staticmethod
+    def backward(ctx, grad_rows):
+        from .fusion import _scatter_raw
+        (ind,) = ctx.saved_tensors
+        shp = ctx.src_shape
+        M = ind.numel()
+        c = int(np.prod(shp[1:], dtype=np.int64)) if len(shp) > 1 else 1
+        locs = torch.zeros((M, 3), dtype=torch.int64, device=ind.device)
+        locs[:, 0] = ind
+        g = _scatter_raw(locs, grad_rows.contiguous().view(M, c), (shp[0], 1, 1), c, 0.0, grad_rows.device, True, False)
+        return g.view(shp), None
+
+
 def gather_rows(src, ind):
-    """`src[ind]` for a contiguous 2-D (or 1-D) tensor of 4- or 8-byte elements and an int64 index list."""
+    """`src[ind]` for a contiguous 2-D (or 1-D) tensor of 4- or 8-byte elements and an int64 index list.  Differentiable
+    w.r.t. a float32 `src` that requires grad (indices must then be unique, as `nonzero_ordered` output is)."""
     _need_cuda(src, "gather_rows")
+    if src.requires_grad and torch.is_grad_enabled() and src.dtype == torch.float32 and src.dim() >= 1:
+        return _GatherRows.apply(src.contiguous(), ind)
+    return _gather_rows_raw(src, ind)
+
+
+def _gather_rows_raw(src, ind):
     dev = src.device
     src = src.contiguous()
     row_shape = tuple(src.shape[1:])

@@ -181,6 +181,11 @@ class _CudaLocalOps:
                                            grad_out, nchw=True, count=count, cell_hist=hs, out=out)
 
 
+def grad_exchange_name():
+    """Which collective `back_project_voxel_sharded`'s backward uses for grad_feats (reported by bench.py)."""
+    return "all_reduce"
+
+
 def grad_view_chunks(V, world):
     """View ranges whose gradient slices are all-reduced while the next range is still being computed
     (`D3M_SHARD_GRAD_CHUNKS`, default 1 = one call + one all-reduce: the per-range fixed costs -- scan, pre-division

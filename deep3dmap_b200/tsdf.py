@@ -8,6 +8,7 @@ Constructor arguments, method names, attribute names and return layouts are the 
 integration work happens in `libd3m.so` (`csrc/tsdf.cu`); there is no CPU path.
 """
 import ctypes
+import sys
 
 import numpy as np
 
@@ -44,6 +45,11 @@ class _Handle:
     def __init__(self, dims, origin, voxel_size, trunc, device, x_begin=0):
         _lib.require_device()
         self.ptr = ctypes.c_void_p()
+        if device is None:
+            # the calling thread's current device (after torch.cuda.set_device(local_rank) that is the rank's GPU),
+            # like the reference's pycuda.autoinit / `.cuda()`
+            device = _lib.lib().d3m_current_device()
+        self.device = int(device)
         org = np.ascontiguousarray(origin, dtype=np.float32)
         rc = _lib.lib().d3m_tsdf_create_slab(int(dims[0]), int(dims[1]), int(dims[2]), int(x_begin), _f32p(org),
                                              float(voxel_size), float(trunc), int(device), ctypes.byref(self.ptr))
@@ -60,6 +66,20 @@ class _Handle:
             self.close()
         except Exception:
             pass
+
+    def stream(self, explicit):
+        """Stream of a call on this handle: the one given at construction, else -- when torch is loaded -- torch's current
+        stream on the handle's device AT CALL TIME (so uploads issued through torch and the integrate kernels are
+        ordered), else the legacy default stream."""
+        if explicit is not None:
+            return explicit
+        if "torch" in sys.modules:
+            from .voxel import _raw_stream
+            if _raw_stream is not None:
+                return _raw_stream(self.device)
+            import torch
+            return torch.cuda.current_stream(self.device).cuda_stream
+        return None
 
     def volumes(self):
         t, w, c = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
@@ -98,7 +118,7 @@ class TSDFVolume:
         the same planes of the unsharded volume (see `shard.tsdf_slab` / `shard.gather_tsdf_volume`).
     """
 
-    def __init__(self, vol_bnds, voxel_size, use_gpu=True, margin=5, device=0, integrate_color=False, stream=None,
+    def __init__(self, vol_bnds, voxel_size, use_gpu=True, margin=5, device=None, integrate_color=False, stream=None,
                  slab=None):
         vol_bnds = np.asarray(vol_bnds)
         assert vol_bnds.shape == (3, 2), "[!] `vol_bnds` should be of shape (3, 2)."
@@ -150,7 +170,7 @@ class TSDFVolume:
             cptr = _f32p(col)
             flags |= _lib.TSDF_WITH_COLOR
         rc = _lib.lib().d3m_tsdf_integrate_host(self._h.ptr, _f32p(depth), cptr, im_h, im_w, _f32p(K), _f32p(T),
-                                                float(obs_weight), flags, self._stream)
+                                                float(obs_weight), flags, self._h.stream(self._stream))
         _lib.check(rc, "d3m_tsdf_integrate_host")
         self.gpu_launches += _lib.lib().d3m_tsdf_last_launches(self._h.ptr)
 
@@ -164,9 +184,10 @@ class TSDFVolume:
         if isinstance(depth_ims, np.ndarray):
             import torch
             from .voxel import upload
-            d = upload(torch.from_numpy(np.ascontiguousarray(depth_ims, dtype=np.float32)),
-                       torch.device("cuda", torch.cuda.current_device()))
-            torch.cuda.current_stream().synchronize()  # the handle's stream need not be torch's current one
+            hdev = torch.device("cuda", self._h.device)
+            d = upload(torch.from_numpy(np.ascontiguousarray(depth_ims, dtype=np.float32)), hdev)
+            if self._stream is not None:
+                torch.cuda.current_stream(hdev).synchronize()  # an explicit handle stream is not torch's current one
             keep.append(d)
         else:
             d = depth_ims
@@ -177,19 +198,23 @@ class TSDFVolume:
         if color_ims is not None and self._integrate_color:
             if isinstance(color_ims, np.ndarray):
                 import torch
-                c = torch.from_numpy(np.stack([self._fold_color(ci) for ci in color_ims])).cuda()
+                c = torch.from_numpy(np.stack([self._fold_color(ci) for ci in color_ims])).to(
+                    torch.device("cuda", self._h.device))
+                if self._stream is not None:
+                    torch.cuda.current_stream(c.device).synchronize()
                 keep.append(c)
             else:
                 c = color_ims
             cptr = _dev_ptr(c)
             flags |= _lib.TSDF_WITH_COLOR
         rc = _lib.lib().d3m_tsdf_integrate_device(self._h.ptr, _dev_ptr(d), cptr, F, H, W, _f32p(K), per_frame,
-                                                  _f32p(T), _f32p(ow) if ow is not None else None, flags, self._stream)
+                                                  _f32p(T), _f32p(ow) if ow is not None else None, flags,
+                                                  self._h.stream(self._stream))
         _lib.check(rc, "d3m_tsdf_integrate_device")
         self.gpu_launches += _lib.lib().d3m_tsdf_last_launches(self._h.ptr)
         if keep:
             import torch
-            torch.cuda.synchronize()  # temporaries uploaded here must outlive the launch
+            torch.cuda.synchronize(self._h.device)  # temporaries uploaded here must outlive the launch
 
     # -- results ----------------------------------------------------------------------------------
     def get_volume(self):
@@ -200,7 +225,7 @@ class TSDFVolume:
             self._weight_vol_cpu = np.empty(self._local_dim, dtype=np.float32)
             self._color_vol_cpu = np.empty(self._local_dim, dtype=np.float32)
         rc = _lib.lib().d3m_tsdf_download(self._h.ptr, _f32p(self._tsdf_vol_cpu), _f32p(self._weight_vol_cpu),
-                                          _f32p(self._color_vol_cpu), self._stream)
+                                          _f32p(self._color_vol_cpu), self._h.stream(self._stream))
         _lib.check(rc, "d3m_tsdf_download")
         return self._tsdf_vol_cpu, self._color_vol_cpu, self._weight_vol_cpu
 
@@ -209,7 +234,7 @@ class TSDFVolume:
         return self._h.volumes()
 
     def reset(self):
-        _lib.check(_lib.lib().d3m_tsdf_reset(self._h.ptr, self._stream), "d3m_tsdf_reset")
+        _lib.check(_lib.lib().d3m_tsdf_reset(self._h.ptr, self._h.stream(self._stream)), "d3m_tsdf_reset")
 
     def _marching_cubes(self):
         try:
@@ -258,7 +283,7 @@ class TSDFVolumeTorch:
     properties, but the per-frame work runs on the B200 (half-to-even pixel rounding, cam_z>0, depth>0 --
     i.e. the arithmetic of the torch `integrate()` at :437-482, not of the PyCUDA kernel)."""
 
-    def __init__(self, voxel_dim, origin, voxel_size, margin=3, device=0, stream=None):
+    def __init__(self, voxel_dim, origin, voxel_size, margin=3, device=None, stream=None):
         import torch
         self._torch = torch
         self.device = torch.device("cpu")  # the tensors handed back live on the CPU, as in the reference
@@ -274,7 +299,7 @@ class TSDFVolumeTorch:
         self.gpu_launches = 0
 
     def reset(self):
-        _lib.check(_lib.lib().d3m_tsdf_reset(self._h.ptr, self._stream), "d3m_tsdf_reset")
+        _lib.check(_lib.lib().d3m_tsdf_reset(self._h.ptr, self._h.stream(self._stream)), "d3m_tsdf_reset")
 
     def rebase(self, origin, voxel_size=None, margin=None):
         """Extension: re-use this object (and its device memory) for another volume of the same `voxel_dim` --
@@ -288,7 +313,7 @@ class TSDFVolumeTorch:
         self._vol_origin = origin
         org = np.ascontiguousarray(self._torch.as_tensor(origin).detach().float().cpu().numpy(), dtype=np.float32)
         rc = _lib.lib().d3m_tsdf_rebase(self._h.ptr, _f32p(org), np.float32(self._voxel_size), np.float32(self._sdf_trunc),
-                                        self._stream)
+                                        self._h.stream(self._stream))
         _lib.check(rc, "d3m_tsdf_rebase")
 
     def integrate(self, depth_im, cam_intr, cam_pose, obs_weight):
@@ -300,7 +325,7 @@ class TSDFVolumeTorch:
         depth = np.ascontiguousarray(depth_im.float().cpu().numpy())
         im_h, im_w = depth.shape
         rc = _lib.lib().d3m_tsdf_integrate_host(self._h.ptr, _f32p(depth), None, im_h, im_w, _f32p(K), _f32p(M),
-                                                float(obs_weight), _lib.TSDF_TORCH_SEMANTICS, self._stream)
+                                                float(obs_weight), _lib.TSDF_TORCH_SEMANTICS, self._h.stream(self._stream))
         _lib.check(rc, "d3m_tsdf_integrate_host")
         self.gpu_launches += _lib.lib().d3m_tsdf_last_launches(self._h.ptr)
 
@@ -308,33 +333,40 @@ class TSDFVolumeTorch:
         """Extension: all views of a fragment (`transforms_seq.py:358-363` loop) in one launch."""
         torch = self._torch
         d = depth_ims.float()
+        hdev = torch.device("cuda", self._h.device)
         if not d.is_cuda:
-            d = d.cuda()
+            from .voxel import upload
+            d = upload(d, hdev)
+        elif d.device != hdev:
+            d = d.to(hdev)
         d = d.contiguous()
+        if self._stream is not None:
+            torch.cuda.current_stream(hdev).synchronize()  # an explicit handle stream is not torch's current one
         F, H, W = (int(s) for s in d.shape)
         w2c = torch.stack([torch.inverse(p.float().cpu()) for p in cam_poses]).numpy()
         K, per_frame, T, ow = _frames_args(torch.as_tensor(cam_intr).float().cpu().numpy(), w2c, obs_weights, F)
         rc = _lib.lib().d3m_tsdf_integrate_device(self._h.ptr, d.data_ptr(), None, F, H, W, _f32p(K), per_frame, _f32p(T),
                                                   _f32p(ow) if ow is not None else None, _lib.TSDF_TORCH_SEMANTICS,
-                                                  self._stream)
+                                                  self._h.stream(self._stream))
         _lib.check(rc, "d3m_tsdf_integrate_device")
         self.gpu_launches += _lib.lib().d3m_tsdf_last_launches(self._h.ptr)
-        torch.cuda.synchronize()
+        torch.cuda.synchronize(hdev)
 
     def get_volume(self):
         torch = self._torch
         dims = tuple(self._vol_dim.tolist())
         tsdf = np.empty(dims, dtype=np.float32)
         weight = np.empty(dims, dtype=np.float32)
-        _lib.check(_lib.lib().d3m_tsdf_download(self._h.ptr, _f32p(tsdf), _f32p(weight), None, self._stream),
-                   "d3m_tsdf_download")
+        _lib.check(_lib.lib().d3m_tsdf_download(self._h.ptr, _f32p(tsdf), _f32p(weight), None,
+                                                self._h.stream(self._stream)), "d3m_tsdf_download")
         return torch.from_numpy(tsdf), torch.from_numpy(weight)
 
     def device_volumes(self):
         """Extension: zero-copy CUDA tensors (tsdf, weight) over the handle's volumes (valid while `self` lives)."""
         torch = self._torch
         t, w, _ = self._h.volumes()
-        return torch.as_tensor(t, device="cuda"), torch.as_tensor(w, device="cuda")
+        hdev = torch.device("cuda", self._h.device)
+        return torch.as_tensor(t, device=hdev), torch.as_tensor(w, device=hdev)
 
     @property
     def sdf_trunc(self):

@@ -69,24 +69,29 @@ class _on_device:
 
 
 _ws_cache = {}
+_WS_CACHE_MAX = 4096     # the sparse levels have a new N every fragment: bound the memo (it only saves a ~1 us query)
+
+
+def _memo(key, query):
+    n = _ws_cache.get(key)
+    if n is None:
+        if len(_ws_cache) >= _WS_CACHE_MAX:
+            _ws_cache.clear()
+        n = _ws_cache[key] = query()
+    return n
 
 
 def _new_cell_hist(N, B, V, H, W, dev):
-    key = ("h", N, B, V, H, W)
-    n = _ws_cache.get(key)
-    if n is None:
-        n = _ws_cache[key] = _lib.lib().d3m_back_project_cell_hist_elems(N, B, V, H, W)
+    n = _memo(("h", N, B, V, H, W), lambda: _lib.lib().d3m_back_project_cell_hist_elems(N, B, V, H, W))
     return (torch.empty if N > 0 else torch.zeros)((n,), dtype=torch.int32, device=dev)
 
 
 def _workspace(kind, key, dev):
     """Workspace byte count is a pure function of the shapes: cache the ctypes query; the buffer itself comes
     from torch's caching allocator (stream-ordered reuse, graph-capture safe)."""
-    n = _ws_cache.get((kind,) + key)
-    if n is None:
-        L = _lib.lib()
-        n = L.d3m_back_project_fwd_workspace(*key) if kind == "f" else L.d3m_back_project_bwd_workspace(*key)
-        _ws_cache[(kind,) + key] = n
+    L = _lib.lib()
+    n = _memo((kind,) + key, lambda: L.d3m_back_project_fwd_workspace(*key) if kind == "f"
+              else L.d3m_back_project_bwd_workspace(*key))
     return torch.empty((n,), dtype=torch.uint8, device=dev), n
 
 

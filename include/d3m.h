@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 104
+#define D3M_VERSION 105
 
 enum {
   D3M_OK = 0,
@@ -53,6 +53,8 @@ int d3m_version(void);
 const char* d3m_last_error(void);
 /* number of CUDA devices visible (0 when none / driver missing); never fails */
 int d3m_device_count(void);
+/* the calling thread's current CUDA device (what `.cuda()` / pycuda.autoinit would pick in the reference), -1 without one */
+int d3m_current_device(void);
 
 /* Diagnostics used by bench.py (not part of the reference surface).
  *   d3m_kernel_launches: kernels this library has launched in this process since load.
@@ -153,6 +155,9 @@ int d3m_tsdf_create(int dim_x, int dim_y, int dim_z, const float* origin3_host, 
 int d3m_tsdf_create_slab(int dim_x_local, int dim_y, int dim_z, int x_begin, const float* origin3_host,
                          float voxel_size, float trunc_margin, int device, d3m_tsdf** out_handle);
 int d3m_tsdf_destroy(d3m_tsdf* h);
+/* device ordinal the handle's volumes live on.  Every d3m_tsdf_* call makes that device current for its own duration
+ * and restores the caller's current device before returning. */
+int d3m_tsdf_device(d3m_tsdf* h);
 int d3m_tsdf_reset(d3m_tsdf* h, void* stream);
 /* Re-use a handle for another volume of the same dimensions: new origin / voxel size / truncation, volumes reset
  * (tsdf = 1, weight = colour = 0).  The dataloader transform (transforms_seq.py:355-357) builds three small

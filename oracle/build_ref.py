@@ -1,4 +1,7 @@
-"""TEST INFRASTRUCTURE ONLY -- builds `oracle/_ref/libref_tsdf.so` from the reference's own source.
+"""TEST INFRASTRUCTURE ONLY -- builds `oracle/_ref/libref_tsdf.so` from the reference's own source and stages the
+reference's `back_project.py` (verbatim copy, byte for byte) next to it as `oracle/_ref/back_project.py`, so that
+`bench.py` can time the UNMODIFIED reference function on the GPU box (on CUDA: `reference_gpu`; on the host cores:
+`cpu_baseline.kind = "reference"` / `--impl reference`), where `/root/reference` does not exist.
 
 The reference's TSDF GPU kernel is a CUDA C string that PyCUDA compiles at run
 time (`/root/reference/deep3dmap/core/tsdf/tsdf_volume.py:67-142`).  PyCUDA is
@@ -20,6 +23,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_FILE = "/root/reference/deep3dmap/core/tsdf/tsdf_volume.py"
+REF_BP_FILE = "/root/reference/deep3dmap/core/voxel/back_project.py"
 OUT_DIR = os.path.join(HERE, "_ref")
 
 LAUNCHER = r'''
@@ -71,11 +75,23 @@ def extract_kernel_source():
     return m.group(1)
 
 
+def stage_back_project():
+    """Byte-for-byte copy of the reference's back_project.py into the git-ignored oracle/_ref/ (travels to the GPU box)."""
+    if not os.path.exists(REF_BP_FILE):
+        return None
+    import shutil
+    os.makedirs(OUT_DIR, exist_ok=True)
+    dst = os.path.join(OUT_DIR, "back_project.py")
+    shutil.copyfile(REF_BP_FILE, dst)
+    return dst
+
+
 def build(verbose=True):
     """Returns the path of the built .so, or None when the reference tree is absent."""
     if not os.path.exists(REF_FILE):
         return None
     os.makedirs(OUT_DIR, exist_ok=True)
+    stage_back_project()
     cu = os.path.join(OUT_DIR, "ref_tsdf_kernel.cu")
     so = os.path.join(OUT_DIR, "libref_tsdf.so")
     with open(cu, "w") as f:

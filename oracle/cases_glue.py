@@ -74,6 +74,18 @@ def stub_gru(h, x):
     return h + x
 
 
+def stub_gru_grad(h, x):
+    """non-linear stand-in used by the gradient fixture (`fusion_grad_*`): d/dx depends on x, d/dh != 0"""
+    return h * 0.5 + x * (1.0 + 0.25 * x)
+
+
+def fusion_loss_weights(n_rows, n_cols):
+    """fixed weights of the scalar loss the gradient fixture back-propagates: loss = sum(values_all * w)"""
+    r = np.arange(n_rows, dtype=np.float64)[:, None]
+    c = np.arange(n_cols, dtype=np.float64)[None, :]
+    return np.cos(0.37 * r + 1.3 * c + 0.2).astype(np.float32)
+
+
 def fusion_case(mode, seed=33):
     """A sequence of GRUFusion.forward calls: scene A seen from three overlapping fragment volumes (one call with a
     batch of two fragments), then scene B (map reset; in direct mode the finished scene is exported), at two scales."""

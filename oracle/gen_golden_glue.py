@@ -138,6 +138,8 @@ class _self_mask_shim:
 def gen_fusion():
     _, gf_mod = ref_loader.neucon_modules()
     for mode in cases_glue.FUSION_MODES:
+        if os.path.exists(os.path.join(OUT, "fusion_%s.npz" % mode)) and "--force" not in sys.argv:
+            continue                      # recorded fixtures are kept; --force re-records all of them
         case = cases_glue.fusion_case(mode)
         cfg = case["cfg"]
         direct = mode == "direct"
@@ -196,9 +198,60 @@ def gen_fusion():
               [rec["s%d_gC" % s].shape[0] for s in range(len(case["steps"]))])
 
 
+def gen_fusion_grad():
+    """`fusion_grad_<mode>.npz`: the same fragment sequences with autograd ON -- after every GRUFusion.forward the scalar
+    loss sum(values_all * w) is back-propagated and `values_in.grad` recorded (the gradient the reference carries from
+    the ConvGRU input back to the sparse-conv features, gru_fusion.py:236 -> :96 -> :256)."""
+    _, gf_mod = ref_loader.neucon_modules()
+    for mode in ("full", "current"):
+        path = os.path.join(OUT, "fusion_grad_%s.npz" % mode)
+        if os.path.exists(path) and "--force" not in sys.argv:
+            continue
+        case = cases_glue.fusion_case(mode)
+        cfg = case["cfg"]
+        fusion = gf_mod.GRUFusion.__new__(gf_mod.GRUFusion)
+        torch.nn.Module.__init__(fusion)
+        fusion.cfg = cfg
+        fusion.direct_substitude = False
+        fusion.ch_in = case["ch_in"]
+        fusion.feat_init = 0
+        fusion.n_scales = len(cfg.THRESHOLDS) - 1
+        fusion.scene_name = [None, None, None]
+        fusion.global_origin = [None, None, None]
+        fusion.global_volume = [None, None, None]
+        fusion.target_tsdf_volume = [None, None, None]
+
+        class StubGRU(torch.nn.Module):
+            def forward(self, h, x):
+                return cases_glue.stub_gru_grad(h.F, x.F)
+
+        fusion.fusion_nets = torch.nn.ModuleList([StubGRU() for _ in range(3)])
+        rec = {}
+        with ref_loader.cpu_cuda_shim(), _self_mask_shim():
+            for s, step in enumerate(case["steps"]):
+                inputs = dict(img_metas=step["img_metas"],
+                              vol_origin=torch.from_numpy(step["vol_origin"]),
+                              vol_origin_partial=torch.from_numpy(step["vol_origin_partial"]),
+                              world_to_aligned_camera=torch.from_numpy(step["world_to_aligned_camera"]))
+                if step["with_gt"]:
+                    inputs["occ_list"] = [torch.from_numpy(x) for x in step["occ_list"]]
+                    inputs["tsdf_list"] = [torch.from_numpy(x) for x in step["tsdf_list"]]
+                vin = torch.from_numpy(step["values"]).clone().requires_grad_(True)
+                uc, va, tt, ot = fusion.forward(torch.from_numpy(step["coords"]), vin, inputs, scale=step["scale"],
+                                                outputs=None, save_mesh=False)
+                w = torch.from_numpy(cases_glue.fusion_loss_weights(va.shape[0], va.shape[1]))
+                (va * w).sum().backward()
+                rec["s%d_values" % s] = _np(va)
+                rec["s%d_grad_values_in" % s] = _np(vin.grad)
+        np.savez_compressed(path, **rec)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB ; nonzero grad rows per step",
+              [int((np.abs(rec["s%d_grad_values_in" % s]).sum(1) > 0).sum()) for s in range(len(case["steps"]))])
+
+
 if __name__ == "__main__":
     if not ref_loader.available():
         sys.exit("reference tree not mounted; golden vectors can only be generated in the build container")
     os.makedirs(OUT, exist_ok=True)
     gen_c2f()
     gen_fusion()
+    gen_fusion_grad()

@@ -212,6 +212,38 @@ def test_fusion_matches_reference_run(mode):
     util_glue.check_fusion_sequence(mode, make, state)
 
 
+@pytest.mark.parametrize("mode", ["full", "current"])
+def test_fusion_forward_backpropagates_to_values_in(mode):
+    """gru_fusion.py:236 -> :96 -> :256: the gradient of the ConvGRU input reaches `values_in` (and through it the sparse
+    convs, back_project and the 2D backbone).  Fixture: the unmodified reference class with autograd on
+    (oracle/gen_golden_glue.py::gen_fusion_grad), loss = sum(values_all * w)."""
+    import torch
+    from deep3dmap_b200.fusion import GRUFusion
+    dev = torch.device("cuda:0")
+    g = util_glue.load_golden("fusion_grad_" + mode)
+    case = cases_glue.fusion_case(mode)
+    nets = [lambda h, x, r: cases_glue.stub_gru_grad(h, x)] * 3
+    impl = GRUFusion(case["cfg"], ch_in=case["ch_in"], direct_substitute=False, fusion_nets=nets)
+    for s, step in enumerate(case["steps"]):
+        inputs = dict(img_metas=step["img_metas"], vol_origin=torch.from_numpy(step["vol_origin"]).to(dev),
+                      vol_origin_partial=torch.from_numpy(step["vol_origin_partial"]).to(dev),
+                      world_to_aligned_camera=torch.from_numpy(step["world_to_aligned_camera"]).to(dev))
+        if step["with_gt"]:
+            inputs["occ_list"] = [torch.from_numpy(x).to(dev) for x in step["occ_list"]]
+            inputs["tsdf_list"] = [torch.from_numpy(x).to(dev) for x in step["tsdf_list"]]
+        vin = torch.from_numpy(step["values"]).to(dev).requires_grad_(True)
+        uc, va, tt, ot = impl.forward(torch.from_numpy(step["coords"]).to(dev), vin, inputs, scale=step["scale"])
+        assert va.requires_grad, "step %d: values_all lost its graph" % s
+        np.testing.assert_allclose(va.detach().cpu().numpy(), g["s%d_values" % s], rtol=1e-6, atol=1e-6)
+        w = torch.from_numpy(cases_glue.fusion_loss_weights(va.shape[0], va.shape[1])).to(dev)
+        (va * w).sum().backward()
+        assert vin.grad is not None, "step %d: no gradient reached values_in" % s
+        ref = g["s%d_grad_values_in" % s]
+        got = vin.grad.cpu().numpy()
+        np.testing.assert_array_equal(np.abs(got).sum(1) > 0, np.abs(ref).sum(1) > 0, err_msg="step %d grad support" % s)
+        np.testing.assert_allclose(got, ref, rtol=1e-6, atol=1e-6, err_msg="step %d grad values_in" % s)
+
+
 @pytest.mark.parametrize("dims,c,M", [((96, 96, 96), 24, 60000), ((48, 48, 48), 1, 5000), ((5, 7, 3), 4, 40)])
 def test_sparse_to_dense_and_gather_vs_oracle(T, dims, c, M):
     from deep3dmap_b200 import fusion

@@ -1,0 +1,132 @@
+"""GPU, >= 2 devices: the multi-rank path for real -- two processes, one per GPU, `torch.distributed` over NCCL, the CUDA
+kernels of libd3m.so on every rank (no test double, no emulation on one device):
+
+  * `shard.back_project_voxel_sharded` forward (all-reduce of the fp64 depth sums), `all_gather_rows` of the counts and
+    features, backward (all-reduce / view-owner reduce-scatter of grad_feats) against the UNSHARDED `back_project` run
+    on the same GPU and against the oracle;
+  * TSDF x slabs, one per rank, `gather_tsdf_volume`, against the unsharded volume -- and the handle's device contract
+    (ADVICE round 1): a `TSDFVolume` built after `torch.cuda.set_device(rank)` lives on that rank's GPU and no d3m_tsdf_*
+    call moves the thread's current device.
+
+Skipped on boxes with one GPU (the driver's single-GPU pass); run with `gpurun --gpus 2 -- python -m pytest
+tests/test_gpu_shard_nccl.py -m gpu`.  bench.py repeats the same assertions inside its large-scene leg on every
+torchrun launch, so the driver's 2/4/8-GPU scaling run re-proves them.
+"""
+import os
+import socket
+import traceback
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, errq):
+    try:
+        import torch.distributed as dist
+
+        import oracle
+        from oracle import cases
+        from deep3dmap_b200 import TSDFVolume, back_project, shard
+        from util import assert_close, assert_depth_channel_close
+
+        os.environ["MASTER_ADDR"] = "127.0.0.1"
+        os.environ["MASTER_PORT"] = str(port)
+        torch.cuda.set_device(rank)
+        dev = torch.device("cuda", rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+        # ---- voxel-range sharded back_project, 2 fragments, uneven split ---------------------------------------------
+        inp = cases.bp_level(1, 30001, np.int64, batch=2)
+        N, C = inp["coords"].shape[0], inp["feats"].shape[2]
+        b, e = shard.voxel_range(N, rank, world)
+        sizes = [shard.voxel_range(N, r, world)[1] - shard.voxel_range(N, r, world)[0] for r in range(world)]
+        feats = t(inp["feats"]).requires_grad_(True)
+        vol, cnt = shard.back_project_voxel_sharded(t(inp["coords"][b:e]), t(inp["origin"]), inp["voxel_size"], feats,
+                                                    t(inp["KRcam"]))
+        vol.backward(t(inp["grad_out"][b:e]))
+        full_cnt = shard.all_gather_rows(cnt, sizes=sizes)
+        full_vol = shard.all_gather_rows(vol.detach())          # sizes exchanged by the call
+        ref_feats = t(inp["feats"]).requires_grad_(True)
+        ref_vol, ref_cnt = back_project(t(inp["coords"]), t(inp["origin"]), inp["voxel_size"], ref_feats, t(inp["KRcam"]))
+        ref_vol.backward(t(inp["grad_out"]))
+        assert torch.equal(full_cnt, ref_cnt), "all-gathered count != unsharded count"
+        assert torch.equal(full_vol[:, :C], ref_vol[:, :C].detach()), "all-gathered features != unsharded features"
+        assert_depth_channel_close(full_vol[:, C].cpu().numpy(), ref_vol[:, C].detach().cpu().numpy(), "depth channel")
+        assert_close(feats.grad.cpu().numpy(), ref_feats.grad.cpu().numpy(), "all-reduced grad_feats vs unsharded")
+        o_vol, o_cnt = oracle.back_project_fwd(inp["coords"], inp["origin"], inp["voxel_size"], inp["feats"], inp["KRcam"])
+        o_g = oracle.back_project_bwd(inp["coords"], inp["origin"], inp["voxel_size"], inp["feats"].shape, inp["KRcam"],
+                                      inp["grad_out"])
+        np.testing.assert_array_equal(full_cnt.cpu().numpy(), o_cnt)
+        assert_close(feats.grad.cpu().numpy(), o_g, "all-reduced grad_feats vs oracle")
+
+        # ---- view-owner exchange: every rank ends with the summed gradient of ITS views only -----------------------------
+        if hasattr(shard, "back_project_voxel_sharded_view_owner"):
+            f2 = t(inp["feats"]).requires_grad_(True)
+            vol2, cnt2, grad_fn = shard.back_project_voxel_sharded_view_owner(
+                t(inp["coords"][b:e]), t(inp["origin"]), inp["voxel_size"], f2, t(inp["KRcam"]))
+            assert torch.equal(cnt2, cnt) and torch.equal(vol2, vol.detach())
+            g_own, (v0, v1) = grad_fn(t(inp["grad_out"][b:e]))
+            assert_close(g_own.cpu().numpy(), ref_feats.grad[v0:v1].cpu().numpy(), "owned view range of grad_feats")
+
+        # ---- TSDF x slabs + the device contract -----------------------------------------------------------------------
+        c = cases.tsdf_case("orbit_small")
+        probe = TSDFVolume(c["vol_bnds"].copy(), c["voxel_size"], margin=c["margin"])
+        dimx = int(probe._vol_dim[0])
+        slab = TSDFVolume(c["vol_bnds"].copy(), c["voxel_size"], margin=c["margin"], slab=shard.tsdf_slab(dimx, rank, world))
+        assert slab._h.device == rank and probe._h.device == rank, "handle must live on the rank's current device"
+        depths = np.stack([d for d, _ in c["frames"]])
+        poses = np.stack([p for _, p in c["frames"]])
+        slab.integrate_batch(depths, c["K"], poses, c["obs_weights"])
+        for (depth, pose), w in zip(c["frames"], c["obs_weights"]):
+            probe.integrate(None, depth, c["K"], pose, w)
+        assert torch.cuda.current_device() == rank, "a d3m_tsdf_* call moved the current device"
+        other = TSDFVolume(c["vol_bnds"].copy(), c["voxel_size"], margin=c["margin"], device=(rank + 1) % world)
+        other.integrate(None, depths[0], c["K"], poses[0], 1.0)
+        assert torch.cuda.current_device() == rank, "integrate on a foreign-device handle moved the current device"
+        assert torch.zeros(1, device="cuda").device.index == rank
+        del other
+        lt, lw, _ = slab.device_volumes()
+        ft, fw = shard.gather_tsdf_volume(torch.as_tensor(lt, device=dev), torch.as_tensor(lw, device=dev), dimx)
+        rt, _, rw = probe.get_volume()
+        np.testing.assert_array_equal(fw.cpu().numpy(), rw)
+        np.testing.assert_array_equal(ft.cpu().numpy(), rt)
+        assert (rw > 0).sum() > 1000
+        dist.barrier()
+        dist.destroy_process_group()
+    except Exception:
+        errq.put((rank, traceback.format_exc()))
+        raise
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (run under `gpurun --gpus 2`)")
+def test_two_ranks_nccl_sharded_back_project_and_tsdf_slabs():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    errq = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, errq)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(600)
+    msgs = []
+    while not errq.empty():
+        msgs.append("rank %d:\n%s" % errq.get())
+    alive = [p for p in procs if p.is_alive()]
+    for p in alive:
+        p.kill()
+    assert not msgs, "\n".join(msgs)
+    assert not alive, "a rank hung"
+    assert all(p.exitcode == 0 for p in procs), [p.exitcode for p in procs]
