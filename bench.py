@@ -925,6 +925,8 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
             raise AssertionError("large-scene multi-rank parity FAILED: %r" % (parity,))
     del coords_all, go_all
     torch.cuda.empty_cache()
+    step()   # the allocator re-acquires the step's workspaces (16 GB of entry tables) once, outside the timed region
+    torch.cuda.synchronize()
     S = torch.tensor([float(cnt.double().sum().item())], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(S)

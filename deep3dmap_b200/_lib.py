@@ -31,6 +31,7 @@ SYMBOLS = (
 )
 
 COORDS_F32, COORDS_I64, COORDS_I32 = 0, 1, 2
+FEATS_NHWC, FEATS_NCHW = 0, 1
 TSDF_KERNEL_SEMANTICS, TSDF_TORCH_SEMANTICS, TSDF_WITH_COLOR = 0, 1, 2
 
 _lib = None
@@ -66,9 +67,9 @@ def lib():
     L.d3m_back_project_fwd_workspace.restype = sz
     L.d3m_back_project_cell_hist_elems.argtypes = [i64, i32, i32, i32, i32]
     L.d3m_back_project_cell_hist_elems.restype = sz
-    L.d3m_back_project_fwd.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
+    L.d3m_back_project_fwd.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd.restype = i32
-    L.d3m_back_project_fwd_partial.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
+    L.d3m_back_project_fwd_partial.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd_partial.restype = i32
     L.d3m_back_project_fwd_finish.argtypes = [i64, i32, i32, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd_finish.restype = i32

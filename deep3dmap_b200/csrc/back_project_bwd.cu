@@ -5,14 +5,15 @@
 //
 // The scatter is turned into a gather (texel-centric), so every texel is produced by exactly one lane group
 // in a fixed order:
-//   prep    per voxel: project into every view (same arithmetic as forward), count valid views, histogram the
-//           valid samples per bilinear cell (v,b,y0,x0) with INTEGER atomics, and write the pre-divided rows
-//           ghat[n,:] = grad_out[n,:C]/max(count,1) into a 16-byte aligned (N,C) buffer (grad_out rows are
-//           (C+1) floats and cannot be vector-loaded).
-//   scan    exclusive prefix sum of the cell histogram (two kernels, ticket-finalised chunk sums).
-//   fill    project again, claim a slot in the cell with an integer atomic, store {n, fx, fy} (16 B).
-//   order   sort every cell's entries by voxel index (windowed warp rank-sort; in-place bitonic for cells
-//           with more than 32 entries) -- this removes the only nondeterminism (slot claim order).
+//   hist    histogram of the valid samples per bin = (bilinear cell (v,b,y0,x0), voxel bucket), INTEGER atomics --
+//           normally produced by the forward gather, which projects every voxel anyway (d3m_back_project_fwd(cell_hist));
+//   scan    exclusive prefix sum of the histogram (single pass, decoupled look-back) -- normally done by the
+//           scan CTAs of bp_fwd_finish right after the forward gather;
+//   fill    one launch, two independent jobs: project again, claim a slot of the bin with an integer atomic and store
+//           {n, fx, fy, bin} (16 B); the spare CTAs write the pre-divided rows ghat[n,:] = grad_out[n,:C]/max(count,1)
+//           into a 16-byte aligned (N,C) buffer (grad_out rows are (C+1) floats and cannot be vector-loaded);
+//   order   every bin's entries into ascending voxel order (thread per entry, rank sort, out of place) -- this removes
+//           the only nondeterminism, the claim order of the fill atomics;
 //   gather  CTA per (TY x TX) tile of texels of one map: lane groups walk the (TY+1) x (TX+1) bilinear CELLS that
 //           touch the tile; every entry's ghat row is loaded ONCE (R 128-bit loads per lane) and feeds the four
 //           corner sums nw/ne/sw/se of its cell (fp32 mul + add in entry order).  The 4 per-cell partials go to
@@ -20,15 +21,13 @@
 //           nw(y,x) + ne(y,x-1) + sw(y-1,x) + se(y-1,x-1) and is stored once.  (A texel-centric walk reads every
 //           row four times and was bound by L2->SM load latency.)
 #include <stdlib.h>
+#include <string.h>
 
 #include "d3m_common.cuh"
 
 namespace d3m {
 
 constexpr unsigned kFullB = 0xffffffffu;
-constexpr int kScanThreads = 256;
-constexpr int kScanItems = 8;
-constexpr int kScanChunk = kScanThreads * kScanItems;
 constexpr int kGatherWarps = 8;
 
 struct BwdParams {
@@ -42,19 +41,18 @@ struct BwdParams {
   const float* grad_out;
   const float* count;  // (N,) view counts from the forward pass, or the workspace copy computed by bp_bwd_count_kernel
   float* ghat;
-  int* bin_cnt;          // per-cell histogram: workspace copy, or the one the forward pass produced (read-only then)
-  int* bin_cursor;       // per-cell next free entry position of the fill pass (scan initialises it to bin_start)
-  int* bin_start;  // M+1
-  int4* entries;         // {voxel, fx, fy, cell} in slot-claim order (fill)
-  int4* sorted;          // the same entries, every cell in ascending voxel order (order)
+  int* bin_cnt;          // histogram (BinLayout.cnt): forward's, or this call's workspace copy
+  int* bin_cursor;       // claims per bin of the fill pass; zero on entry, re-zeroed by the gather (BinLayout.cursor)
+  int* bin_start;        // Mb+1, exclusive scan of bin_cnt
+  int4* entries;         // {voxel, fx, fy, bin} in slot-claim order (fill)
+  int4* sorted;          // the same entries, every bin in ascending voxel order (gather phase 0)
   float* grad_feats;
   int64_t M;      // V*B*H*W cells
   int64_t Mb;     // M << nb_log2 bins (cell-major, voxel-bucket-minor; see BinCfg)
   int nb_log2;
-  unsigned long long* scan_state;  // nchunks words, zeroed together with bin_cnt
-  unsigned int* counter;           // scan ticket, zeroed together with bin_cnt
-  int nchunks;
   int grad_nchw;                   // 1: gather writes (V,B,C,H,W) directly
+  // fill + ghat launch
+  int fill_ctas_x, fill_ctas;      // voxel CTAs per view group; fill CTAs in total (the CTAs behind them write ghat)
 };
 
 constexpr int kSampleThreads = 256;
@@ -83,17 +81,14 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_count_kernel(const BwdP
   cnt_out[n] = (float)cnt;
 }
 
-// One thread per (voxel, group of kViewsPerThread views): blockIdx.y = view group.  Short dependency chains and N*V-way parallelism instead of
+// One thread per (voxel, group of kViewsPerThread views).  Short dependency chains and N*V-way parallelism instead of
 // a 9-deep serial loop per voxel (these passes are latency-bound at fragment size).
-//   FILL = false: histogram the valid samples per bilinear cell (integer RED).  Skipped entirely when the forward
-//                 pass already produced the histogram (d3m_back_project_fwd(..., cell_hist)).
-//   FILL = true : claim the cell's next entry position (one integer atomic on the cursor), store {n, fx, fy, cell}.
+//   FILL = false: histogram the valid samples per bin (integer RED).  Only when the forward pass did not already
+//                 produce the histogram (d3m_back_project_fwd(..., cell_hist)).
+//   FILL = true : claim the bin's next entry position (one integer atomic on the cursor), store {n, fx, fy, bin}.
 constexpr int kViewsPerThread = 3;  // independent atomics in flight per thread (the pass is latency-bound on them)
 template <int KIND, bool FILL>
-__global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const BwdParams p) {
-  pdl_enter();
-  const int v0 = blockIdx.y * kViewsPerThread;
-  const int64_t n = (int64_t)blockIdx.x * kSampleThreads + threadIdx.x;
+__device__ __forceinline__ void sample_pass(const BwdParams& p, const int64_t n, const int v0) {
   if (n >= p.N) return;
   float cx, cy, cz;
   const int b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
@@ -125,173 +120,83 @@ __global__ void __launch_bounds__(kSampleThreads) bp_bwd_sample_kernel(const Bwd
   } else {
     int pos[kViewsPerThread];
 #pragma unroll
-    for (int j = 0; j < kViewsPerThread; ++j)   // claim order is arbitrary; `order` fixes it
-      pos[j] = ok[j] ? atomicAdd(p.bin_cursor + key[j], 1) : 0;
+    for (int j = 0; j < kViewsPerThread; ++j)   // claim order is arbitrary; the gather's phase 0 fixes it
+      pos[j] = ok[j] ? __ldg(p.bin_start + key[j]) + atomicAdd(p.bin_cursor + key[j], 1) : 0;
 #pragma unroll
     for (int j = 0; j < kViewsPerThread; ++j)
       if (ok[j]) p.entries[pos[j]] = make_int4((int)n, __float_as_int(fx[j]), __float_as_int(fy[j]), key[j]);
   }
 }
 
-// ---- exclusive scan of the cell histogram: ONE pass, chained look-back ---------------------------
-// CTAs take chunk ids from a ticket (so a chunk's predecessors are always already scheduled), publish their
-// aggregate, walk back over predecessors until they meet an inclusive prefix, then publish their own.
-// state word = (flag << 32) | value, flag 0 = not ready, 1 = aggregate, 2 = inclusive prefix.  Integer sums:
-// the result does not depend on the order in which CTAs arrive.
-//
-// The same launch carries the independent pre-division pass in its CTAs >= nchunks:
-//   ghat[n,c] = grad_out[n,c] / max(count[n],1)   (div backward of back_project.py:72), re-packed to 16-byte aligned
-//   rows of C floats (grad_out rows are (C+1) floats and cannot be vector-loaded).
-__global__ void __launch_bounds__(kScanThreads) bp_scan_ghat_kernel(const BwdParams p) {
+template <int KIND>
+__global__ void __launch_bounds__(kSampleThreads) bp_bwd_hist_kernel(const BwdParams p) {
   pdl_enter();
-  __shared__ int red[kScanThreads / 32];
-  __shared__ int s_cid, s_prefix;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if ((int)blockIdx.x >= p.nchunks) {
-    const int C = p.C, C1 = C + 1;
-    const int64_t wg = (int64_t)(blockIdx.x - p.nchunks) * (kScanThreads / 32) + warp;
-    if ((C & 3) == 0 && C <= 128) {
-      // lane <-> (row, channel quad): 32/(C/4) rows per warp step, kGhatSteps steps in flight; 4 scalar loads (rows of
-      // C+1 floats are unaligned), one 128-bit store per lane
-      const int C4 = C >> 2;
-      const int rows_per_step = 32 / C4;
-      const int rl = lane / C4, j = lane - rl * C4;
-      const bool lane_on = rl < rows_per_step;
-      const int64_t r0 = wg * (int64_t)(rows_per_step * kGhatSteps) + rl;
-      float4 g[kGhatSteps];
-      float d[kGhatSteps];
+  sample_pass<KIND, false>(p, (int64_t)blockIdx.x * kSampleThreads + threadIdx.x, blockIdx.y * kViewsPerThread);
+}
+
+// ghat[n,c] = grad_out[n,c] / max(count[n],1)   (div backward of back_project.py:72), re-packed to 16-byte aligned
+// rows of C floats.  `wg` = global warp index of this job.
+__device__ __forceinline__ void ghat_rows(const BwdParams& p, const int64_t wg, const int lane) {
+  const int C = p.C, C1 = C + 1;
+  if ((C & 3) == 0 && C <= 128) {
+    // lane <-> (row, channel quad): 32/(C/4) rows per warp step, kGhatSteps steps in flight; 4 scalar loads (rows of
+    // C+1 floats are unaligned), one 128-bit store per lane
+    const int C4 = C >> 2;
+    const int rows_per_step = 32 / C4;
+    const int rl = lane / C4, j = lane - rl * C4;
+    const bool lane_on = rl < rows_per_step;
+    const int64_t r0 = wg * (int64_t)(rows_per_step * kGhatSteps) + rl;
+    float4 g[kGhatSteps];
+    float d[kGhatSteps];
 #pragma unroll
-      for (int k = 0; k < kGhatSteps; ++k) {
-        const int64_t r = r0 + (int64_t)k * rows_per_step;
-        g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        d[k] = 1.0f;
-        if (lane_on && r < p.N) {
-          const float* src = p.grad_out + r * C1 + 4 * j;
-          g[k] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
-          d[k] = fmaxf(__ldg(p.count + r), 1.0f);
-        }
-      }
-#pragma unroll
-      for (int k = 0; k < kGhatSteps; ++k) {
-        const int64_t r = r0 + (int64_t)k * rows_per_step;
-        if (lane_on && r < p.N)
-          reinterpret_cast<float4*>(p.ghat)[r * C4 + j] =
-              make_float4(__fdiv_rn(g[k].x, d[k]), __fdiv_rn(g[k].y, d[k]), __fdiv_rn(g[k].z, d[k]), __fdiv_rn(g[k].w, d[k]));
-      }
-    } else {
-      // any C: warp per row, lanes stride over the channels
-      const int64_t r0 = wg * kGhatSteps;
-      for (int k = 0; k < kGhatSteps; ++k) {
-        const int64_t r = r0 + k;
-        if (r >= p.N) break;
-        const float d = fmaxf(__ldg(p.count + r), 1.0f);
-        for (int c = lane; c < C; c += 32) p.ghat[r * C + c] = __fdiv_rn(__ldg(p.grad_out + r * C1 + c), d);
+    for (int k = 0; k < kGhatSteps; ++k) {
+      const int64_t r = r0 + (int64_t)k * rows_per_step;
+      g[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+      d[k] = 1.0f;
+      if (lane_on && r < p.N) {
+        const float* src = p.grad_out + r * C1 + 4 * j;
+        g[k] = make_float4(__ldg(src), __ldg(src + 1), __ldg(src + 2), __ldg(src + 3));
+        d[k] = fmaxf(__ldg(p.count + r), 1.0f);
       }
     }
-    return;
-  }
-  if (tid == 0) s_cid = (int)atomicAdd(p.counter, 1u);
-  __syncthreads();
-  const int cid = s_cid;
-  const int64_t base = (int64_t)cid * kScanChunk + (int64_t)tid * kScanItems;
-  int v[kScanItems];
-  if (base + kScanItems <= p.Mb) {
-    const int4* q = reinterpret_cast<const int4*>(p.bin_cnt + base);
 #pragma unroll
-    for (int i = 0; i < kScanItems / 4; ++i) {
-      const int4 t = q[i];
-      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    for (int k = 0; k < kGhatSteps; ++k) {
+      const int64_t r = r0 + (int64_t)k * rows_per_step;
+      if (lane_on && r < p.N)
+        reinterpret_cast<float4*>(p.ghat)[r * C4 + j] =
+            make_float4(__fdiv_rn(g[k].x, d[k]), __fdiv_rn(g[k].y, d[k]), __fdiv_rn(g[k].z, d[k]), __fdiv_rn(g[k].w, d[k]));
     }
   } else {
-#pragma unroll
-    for (int i = 0; i < kScanItems; ++i) v[i] = (base + i < p.Mb) ? p.bin_cnt[base + i] : 0;
-  }
-  int s = 0;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i) s += v[i];
-  int inc = s;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int t = __shfl_up_sync(kFullB, inc, o);
-    if (lane >= o) inc += t;
-  }
-  if (lane == 31) red[warp] = inc;
-  __syncthreads();
-  int woff = 0, total = 0;
-#pragma unroll
-  for (int w = 0; w < kScanThreads / 32; ++w) {
-    if (w < warp) woff += red[w];
-    total += red[w];
-  }
-  if (warp == 0) {
-    // decoupled look-back, one warp wide: lane l inspects chunk cid-1-l; the nearest predecessor that already holds an
-    // inclusive prefix (state 2) ends the walk, the aggregates (state 1) in front of it are summed with one shuffle tree.
-    // Ticketed chunk ids guarantee that every predecessor is running, so the spin terminates.
-    volatile unsigned long long* st = p.scan_state;
-    int prefix = 0;
-    if (cid == 0) {
-      if (lane == 0) st[0] = (2ull << 32) | (unsigned)total;
-    } else {
-      if (lane == 0) {
-        st[cid] = (1ull << 32) | (unsigned)total;
-        __threadfence();
-      }
-      for (int j0 = cid - 1;; j0 -= 32) {
-        const int j = j0 - lane;
-        unsigned long long w = 2ull << 32;  // "chunk -1": inclusive prefix 0
-        if (j >= 0) {
-          do { w = st[j]; } while ((w >> 32) == 0ull);
-        }
-        const unsigned done = __ballot_sync(kFullB, (w >> 32) == 2ull);
-        const int first = __ffs(done) - 1;  // -1: no inclusive prefix in this window
-        int use = (done == 0u || lane <= first) ? (int)(unsigned)(w & 0xffffffffull) : 0;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) use += __shfl_xor_sync(kFullB, use, o);
-        prefix += use;
-        if (done != 0u) break;
-      }
-      if (lane == 0) st[cid] = (2ull << 32) | (unsigned)(prefix + total);
+    // any C: warp per row, lanes stride over the channels
+    const int64_t r0 = wg * kGhatSteps;
+    for (int k = 0; k < kGhatSteps; ++k) {
+      const int64_t r = r0 + k;
+      if (r >= p.N) break;
+      const float d = fmaxf(__ldg(p.count + r), 1.0f);
+      for (int c = lane; c < C; c += 32) p.ghat[r * C + c] = __fdiv_rn(__ldg(p.grad_out + r * C1 + c), d);
     }
-    if (lane == 0) {
-      s_prefix = prefix;
-      if (cid == p.nchunks - 1) p.bin_start[p.Mb] = prefix + total;
-    }
-  }
-  __syncthreads();
-  int off = s_prefix + woff + inc - s;
-#pragma unroll
-  for (int i = 0; i < kScanItems; ++i) {
-    if (base + i < p.Mb) {
-      p.bin_start[base + i] = off;
-      p.bin_cursor[base + i] = off;
-    }
-    off += v[i];
   }
 }
 
-// ---- order: every cell's entries into ascending voxel order ----------------------------------------
-// One thread per entry, out of place: rank = number of entries of the same cell with a smaller voxel index (voxel
-// indices are unique within a cell because a voxel projects into a view at most once), destination = cell start +
-// rank.  The lanes of a warp mostly sit in the same cell, so the k reads of the rank loop are L1 broadcasts.
-// This removes the only nondeterminism of the backward pass (the claim order of the fill atomics).
-constexpr int kOrderThreads = 256;
-__global__ void __launch_bounds__(kOrderThreads) bp_bwd_order_kernel(const BwdParams p) {
+// ONE launch, two independent jobs: CTAs [0, fill_ctas) run the fill pass (CTA i <-> voxel block i % fill_ctas_x, view
+// group i / fill_ctas_x), the CTAs behind them the pre-division pass.
+template <int KIND>
+__global__ void __launch_bounds__(kSampleThreads) bp_bwd_fill_ghat_kernel(const BwdParams p) {
   pdl_enter();
-  const int total = __ldg(p.bin_start + p.Mb);
-  for (int i = blockIdx.x * kOrderThreads + threadIdx.x; i < total; i += gridDim.x * kOrderThreads) {
-    const int4 e = __ldg(p.entries + i);
-    const int ms = __ldg(p.bin_start + e.w), me = __ldg(p.bin_start + e.w + 1);
-    int rank = 0;
-    const int* keys = reinterpret_cast<const int*>(p.entries);
-    int j = ms;
-    for (; j + 4 <= me; j += 4) {
-      const int a0 = __ldg(keys + 4 * j), a1 = __ldg(keys + 4 * j + 4), a2 = __ldg(keys + 4 * j + 8),
-                a3 = __ldg(keys + 4 * j + 12);
-      rank += (a0 < e.x) + (a1 < e.x) + (a2 < e.x) + (a3 < e.x);
-    }
-    for (; j < me; ++j) rank += (__ldg(keys + 4 * j) < e.x) ? 1 : 0;
-    p.sorted[ms + rank] = e;
+  const int i = blockIdx.x;
+  if (i < p.fill_ctas) {
+    const int bx = i % p.fill_ctas_x, by = i / p.fill_ctas_x;
+    sample_pass<KIND, true>(p, (int64_t)bx * kSampleThreads + threadIdx.x, by * kViewsPerThread);
+    return;
   }
+  ghat_rows(p, (int64_t)(i - p.fill_ctas) * (kSampleThreads / 32) + (threadIdx.x >> 5), threadIdx.x & 31);
+}
+
+// legacy path (no forward histogram): scan as a kernel of its own
+struct ScanOnly { BinState bins; };
+__global__ void __launch_bounds__(kScanThreads) bp_bwd_scan_kernel(const ScanOnly p) {
+  pdl_enter();
+  scan_bins_cta(p.bins);
 }
 
 // ---- gather --------------------------------------------------------------------------------------
@@ -510,6 +415,44 @@ __global__ void __launch_bounds__(kGatherWarps * 32, (R == 1 ? 4 : 3)) bp_bwd_ga
       }
     }
   }
+  // the cells whose texel (cy, cx) lies in this tile are owned by it: hand their claim counters back as zeros, so that
+  // the binning state can serve another backward call (BinLayout).  Last, off the critical path: plain stores.
+  for (int r = 0; r < TY; ++r) {
+    const int cy = y0 + r;
+    if (cy >= p.H) break;
+    const int cxb = min(x0 + TX, p.W);
+    const int64_t b0 = (map_base + (int64_t)cy * p.W + x0) << p.nb_log2;
+    const int nbins = (cxb - x0) << p.nb_log2;
+    for (int k = threadIdx.x; k < nbins; k += kGatherWarps * 32) p.bin_cursor[b0 + k] = 0;
+  }
+}
+
+// ---- order: every bin's entries into ascending voxel order ----------------------------------------
+// One thread per entry, out of place: rank = number of entries of the same bin with a smaller voxel index (voxel
+// indices are unique within a bin because a voxel projects into a view at most once), destination = bin start +
+// rank.  The lanes of a warp mostly sit in the same bin, so the k reads of the rank loop are L1 broadcasts.
+// This removes the only nondeterminism of the backward pass (the claim order of the fill atomics).
+// (Ranking inside the gather kernel instead -- one launch fewer -- was measured and dropped: per tile only a few hundred
+// entries keep 256 threads busy, the halo cells are ranked twice and the whole CTA waits for its longest bin:
+// fragment level 2 45 -> 61 us, dense level 2 106 -> 165 us, large scene 3.2 -> 5.6 ms; profiles/r02b_bench.json.)
+constexpr int kOrderThreads = 256;
+__global__ void __launch_bounds__(kOrderThreads) bp_bwd_order_kernel(const BwdParams p) {
+  pdl_enter();
+  const int total = __ldg(p.bin_start + p.Mb);
+  for (int i = blockIdx.x * kOrderThreads + threadIdx.x; i < total; i += gridDim.x * kOrderThreads) {
+    const int4 e = __ldg(p.entries + i);
+    const int ms = __ldg(p.bin_start + e.w), me = __ldg(p.bin_start + e.w + 1);
+    int rank = 0;
+    const int* keys = reinterpret_cast<const int*>(p.entries);
+    int j = ms;
+    for (; j + 4 <= me; j += 4) {
+      const int a0 = __ldg(keys + 4 * j), a1 = __ldg(keys + 4 * j + 4), a2 = __ldg(keys + 4 * j + 8),
+                a3 = __ldg(keys + 4 * j + 12);
+      rank += (a0 < e.x) + (a1 < e.x) + (a2 < e.x) + (a3 < e.x);
+    }
+    for (; j < me; ++j) rank += (__ldg(keys + 4 * j) < e.x) ? 1 : 0;
+    p.sorted[ms + rank] = e;
+  }
 }
 
 // any C: one warp per texel, lanes stride over channels
@@ -562,30 +505,18 @@ __global__ void __launch_bounds__(kGatherWarps * 32) bp_bwd_gather_generic_kerne
 
 // ---- host ----------------------------------------------------------------------------------------
 struct BwdWs {
-  size_t ghat, cnt, bin_cnt, bin_cursor, bin_start, scan_state, counter, entries, sorted, total, zero_bytes;
-  int nchunks;
-  int64_t M, Mb;
-  BinCfg bc;
+  size_t ghat, cnt, state, entries, sorted, total;
+  BinLayout bl;
 };
 
 static BwdWs bwd_ws_layout(int64_t N, int B, int V, int C, int H, int W) {
   BwdWs w;
-  w.M = (int64_t)V * B * H * W;
-  w.bc = bin_config(N, V, w.M);
-  w.Mb = w.M << w.bc.nb_log2;
-  w.nchunks = (int)((w.Mb + kScanChunk - 1) / kScanChunk);
+  w.bl = bin_layout(N, B, V, H, W);
   size_t o = 0;
   const size_t n1 = (size_t)(N > 0 ? N : 1);
   w.ghat = o; o = align_up(o + sizeof(float) * n1 * (size_t)C, 256);
   w.cnt = o; o = align_up(o + sizeof(float) * n1, 256);
-  // scan_state and the ticket are cleared by ONE memset; bin_cnt follows them so that the same memset also
-  // clears the histogram when the forward pass did not hand one over
-  w.scan_state = o; o = align_up(o + sizeof(unsigned long long) * (size_t)(w.nchunks + 1), 256);
-  w.counter = o; o = align_up(o + 256, 256);
-  w.bin_cnt = o; o = align_up(o + sizeof(int) * (size_t)w.Mb, 256);
-  w.zero_bytes = o - w.scan_state;
-  w.bin_cursor = o; o = align_up(o + sizeof(int) * (size_t)w.Mb, 256);
-  w.bin_start = o; o = align_up(o + sizeof(int) * (size_t)(w.Mb + 1), 256);
+  w.state = o; o = align_up(o + sizeof(int) * w.bl.total, 256);   // binning state when forward did not hand one over
   w.entries = o; o = align_up(o + sizeof(int4) * n1 * (size_t)V, 256);
   w.sorted = o; o = align_up(o + sizeof(int4) * n1 * (size_t)V, 256);
   w.total = o;
@@ -631,40 +562,46 @@ static void pick_gather_tile(int C, int& TX, int& TY, size_t& smem) {
   }
 }
 
+// `own_state`: the binning state lives in this call's workspace (no forward histogram): clear, histogram and scan it here.
 template <int KIND>
-static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bool have_hist, float* cnt_ws,
+static int launch_bwd(BwdParams p, const BinState& bins, const BinLayout& bl, bool own_state, float* cnt_ws,
                       cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  {
-    const int zrc = zero_async(zero_from, zero_bytes, stream);
-    if (zrc != D3M_OK) return zrc;
-  }
   const unsigned vox_ctas = (unsigned)((p.N + kSampleThreads - 1) / kSampleThreads);
+  const unsigned vgroups = (unsigned)((p.V + kViewsPerThread - 1) / kViewsPerThread);
   if (cnt_ws) {  // no forward count handed over: recompute it
     LaunchScope ls("bp_bwd_count", stream);
     launch_k(bp_bwd_count_kernel<KIND>, dim3(vox_ctas), dim3(kSampleThreads), 0, stream, p, cnt_ws);
+    D3M_CUDA_CHECK(cudaGetLastError());
   }
-  D3M_CUDA_CHECK(cudaGetLastError());
-  if (!have_hist) {
-    LaunchScope ls("bp_bwd_hist", stream);
-    launch_k(bp_bwd_sample_kernel<KIND, false>, dim3(vox_ctas, (p.V + kViewsPerThread - 1) / kViewsPerThread), dim3(kSampleThreads), 0, stream, p);
+  if (own_state) {
+    const int zrc = zero_async(bins.cnt, sizeof(int) * bl.zero_elems, stream);
+    if (zrc != D3M_OK) return zrc;
+    {
+      LaunchScope ls("bp_bwd_hist", stream);
+      launch_k(bp_bwd_hist_kernel<KIND>, dim3(vox_ctas, vgroups), dim3(kSampleThreads), 0, stream, p);
+      D3M_CUDA_CHECK(cudaGetLastError());
+    }
+    ScanOnly so;
+    so.bins = bins;
+    LaunchScope ls("bp_bwd_scan", stream);
+    launch_k(bp_bwd_scan_kernel, dim3((unsigned)bl.nchunks), dim3(kScanThreads), 0, stream, so);
+    D3M_CUDA_CHECK(cudaGetLastError());
   }
-  D3M_CUDA_CHECK(cudaGetLastError());
   {
     const int rows_per_step = ((p.C & 3) == 0 && p.C <= 128) ? 32 / (p.C >> 2) : 1;
-    const int64_t rows_per_cta = (int64_t)(kScanThreads / 32) * kGhatSteps * rows_per_step;
+    const int64_t rows_per_cta = (int64_t)(kSampleThreads / 32) * kGhatSteps * rows_per_step;
     const int64_t ghat_blocks = (p.N + rows_per_cta - 1) / rows_per_cta;
-    LaunchScope ls("bp_bwd_scan_ghat", stream);
-    launch_k(bp_scan_ghat_kernel, dim3((unsigned)(p.nchunks + ghat_blocks)), dim3(kScanThreads), 0, stream, p);
+    const int64_t fill_ctas = (int64_t)vox_ctas * vgroups;
+    D3M_REQUIRE(fill_ctas + ghat_blocks < (1ll << 31), D3M_ERR_ARG, "back_project backward: too many fill CTAs");
+    p.fill_ctas_x = (int)vox_ctas;
+    p.fill_ctas = (int)fill_ctas;
+    LaunchScope ls("bp_bwd_fill_ghat", stream);
+    launch_k(bp_bwd_fill_ghat_kernel<KIND>, dim3((unsigned)(fill_ctas + ghat_blocks)), dim3(kSampleThreads), 0, stream, p);
+    D3M_CUDA_CHECK(cudaGetLastError());
   }
-  D3M_CUDA_CHECK(cudaGetLastError());
-  {
-    LaunchScope ls("bp_bwd_fill", stream);
-    launch_k(bp_bwd_sample_kernel<KIND, true>, dim3(vox_ctas, (p.V + kViewsPerThread - 1) / kViewsPerThread), dim3(kSampleThreads), 0, stream, p);
-  }
-  D3M_CUDA_CHECK(cudaGetLastError());
   {
     int64_t ctas = (p.N * p.V + kOrderThreads - 1) / kOrderThreads;  // upper bound of the entry count (known on device only)
     if (ctas > (int64_t)sms * 16) ctas = (int64_t)sms * 16;
@@ -691,9 +628,13 @@ static int launch_bwd(const BwdParams& p, void* zero_from, size_t zero_bytes, bo
     int64_t ctas = (p.M + kGatherWarps - 1) / kGatherWarps;
     if (ctas > (int64_t)sms * 16) ctas = (int64_t)sms * 16;
     if (ctas < 1) ctas = 1;
-    LaunchScope ls("bp_bwd_gather", stream);
-    launch_k(bp_bwd_gather_generic_kernel, dim3((unsigned)ctas), dim3(kGatherWarps * 32), 0, stream, p);
-    D3M_CUDA_CHECK(cudaGetLastError());
+    {
+      LaunchScope ls("bp_bwd_gather", stream);
+      launch_k(bp_bwd_gather_generic_kernel, dim3((unsigned)ctas), dim3(kGatherWarps * 32), 0, stream, p);
+      D3M_CUDA_CHECK(cudaGetLastError());
+    }
+    const int zrc = zero_async(bins.cursor, sizeof(int) * (size_t)bl.Mb, stream);  // the tile kernel does this itself
+    if (zrc != D3M_OK) return zrc;
   }
   return D3M_OK;
 }
@@ -709,7 +650,7 @@ extern "C" size_t d3m_back_project_bwd_workspace(int64_t N, int B, int V, int C,
 
 extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                                     float voxel_size, int V, int C, int H, int W, const float* KRcam,
-                                    const float* grad_out, const float* count, const int* cell_hist,
+                                    const float* grad_out, const float* count, int* cell_hist,
                                     float* grad_feats_nhwc, int grad_nchw, void* workspace, size_t workspace_bytes,
                                     void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
@@ -724,7 +665,7 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
   D3M_REQUIRE(grad_feats_nhwc && workspace, D3M_ERR_ARG, "back_project backward: NULL pointer");
   const BwdWs w = bwd_ws_layout(N, B, V, C, H, W);
   if (N == 0) {
-    D3M_CUDA_CHECK(cudaMemsetAsync(grad_feats_nhwc, 0, sizeof(float) * (size_t)w.M * C, stream));
+    D3M_CUDA_CHECK(cudaMemsetAsync(grad_feats_nhwc, 0, sizeof(float) * (size_t)w.bl.M * C, stream));
     return D3M_OK;
   }
   D3M_REQUIRE(coords && origin && KRcam && grad_out, D3M_ERR_ARG, "back_project backward: NULL pointer");
@@ -734,28 +675,24 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
   D3M_REQUIRE(workspace_bytes >= w.total, D3M_ERR_WORKSPACE, "back_project backward: workspace %zu < %zu",
               workspace_bytes, w.total);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
+  const bool own_state = cell_hist == nullptr;
+  const BinState bins = bin_state(own_state ? reinterpret_cast<int*>(ws + w.state) : cell_hist, w.bl);
   BwdParams p;
+  memset(&p, 0, sizeof(p));
   p.coords = coords; p.N = N; p.origin = origin; p.B = B; p.vs = voxel_size;
   p.V = V; p.C = C; p.H = H; p.W = W; p.KR = KRcam; p.grad_out = grad_out;
   p.ghat = reinterpret_cast<float*>(ws + w.ghat);
-  // with a forward-pass histogram the workspace copy is unused and only scan_state + ticket need clearing
-  p.bin_cnt = cell_hist ? const_cast<int*>(cell_hist) : reinterpret_cast<int*>(ws + w.bin_cnt);
-  p.bin_cursor = reinterpret_cast<int*>(ws + w.bin_cursor);
-  p.bin_start = reinterpret_cast<int*>(ws + w.bin_start);
-  p.scan_state = reinterpret_cast<unsigned long long*>(ws + w.scan_state);
-  p.counter = reinterpret_cast<unsigned int*>(ws + w.counter);
+  p.bin_cnt = bins.cnt;
+  p.bin_cursor = bins.cursor;
+  p.bin_start = bins.start;
   p.entries = reinterpret_cast<int4*>(ws + w.entries);
   p.sorted = reinterpret_cast<int4*>(ws + w.sorted);
   p.grad_feats = grad_feats_nhwc;
-  p.M = w.M; p.Mb = w.Mb; p.nb_log2 = w.bc.nb_log2;
-  p.nchunks = w.nchunks;
+  p.M = w.bl.M; p.Mb = w.bl.Mb; p.nb_log2 = w.bl.nb_log2;
   p.grad_nchw = grad_nchw ? 1 : 0;
   float* cnt_ws = count ? nullptr : reinterpret_cast<float*>(ws + w.cnt);
   p.count = count ? count : cnt_ws;
-  void* zero_from = ws + w.scan_state;
-  const size_t zero_bytes = cell_hist ? (w.bin_cnt - w.scan_state) : w.zero_bytes;
-  const bool hh = cell_hist != nullptr;
-  if (coords_kind == D3M_COORDS_F32) return launch_bwd<D3M_COORDS_F32>(p, zero_from, zero_bytes, hh, cnt_ws, stream);
-  if (coords_kind == D3M_COORDS_I64) return launch_bwd<D3M_COORDS_I64>(p, zero_from, zero_bytes, hh, cnt_ws, stream);
-  return launch_bwd<D3M_COORDS_I32>(p, zero_from, zero_bytes, hh, cnt_ws, stream);
+  if (coords_kind == D3M_COORDS_F32) return launch_bwd<D3M_COORDS_F32>(p, bins, w.bl, own_state, cnt_ws, stream);
+  if (coords_kind == D3M_COORDS_I64) return launch_bwd<D3M_COORDS_I64>(p, bins, w.bl, own_state, cnt_ws, stream);
+  return launch_bwd<D3M_COORDS_I32>(p, bins, w.bl, own_state, cnt_ws, stream);
 }

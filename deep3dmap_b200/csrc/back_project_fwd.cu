@@ -39,9 +39,15 @@ struct FwdParams {
   float* count;
   float* zbar;
   int* bidx;
-  unsigned int* counter;  // zeroed here for the stats kernel
+  unsigned int* counter;  // ticket of the depth statistics (zero on entry: cleared by the prep kernel, re-cleared by its user)
   int* cell_hist;         // optional histogram of valid samples per (bilinear cell, voxel bucket) bin, consumed by backward
   int nb_log2;            // BinCfg of this call
+  // depth statistics fused into this kernel (single-fragment calls): one fp64 (s, s2, n) triple per CTA
+  int fuse_stats;
+  double* partial;        // (gridDim.x, 3)
+  float* stats;           // (B, 2): mean, sd
+  double* sums;           // (B, 3) or NULL (voxel-range sharding: handed to the caller instead of finalising)
+  int finalize;
   int tv;
   int vchunk;
   int64_t num_tiles;
@@ -96,6 +102,90 @@ __device__ __forceinline__ float corner_chain(float t00, float t01, float t10, f
   return __fmaf_rn(t11, se, __fmaf_rn(t10, sw, __fmaf_rn(t01, ne, __fmul_rn(t00, nw))));
 }
 
+// mean / sd of back_project.py:77-78 from the three fp64 sums
+__device__ __forceinline__ void stats_from_sums(double s, double s2, double c, float& mean, float& sd) {
+  if (c > 0.0) {
+    mean = (float)(s / c);
+    const double m = (double)mean;
+    double ssq = s2 - 2.0 * m * s + c * m * m;
+    if (ssq < 0.0) ssq = 0.0;
+    sd = __fadd_rn((float)sqrt(ssq), 1e-5f);
+  } else {
+    mean = __int_as_float(0x7fc00000);  // mean of an empty set is NaN in the reference; never used (z<=0 -> 0)
+    sd = 1e-5f;
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
+  return v;
+}
+
+// Depth statistics of a single-fragment call, fused into the gather kernel: every lane sums the mean depths of ITS
+// voxels over the warp's tiles in fp64, one shuffle tree per warp, the four warps of the CTA in order, ONE (s, s2, n)
+// triple per CTA in global memory.  The triples are folded by whoever needs the result (every CTA of bp_fwd_finish for
+// itself: see fold_partials) -- a "last CTA folds" ticket here was measured: the serial fold of a few thousand triples by
+// one CTA sits at the tail of the gather kernel (+6 us on every level).  The tile sequence of a warp and both trees are
+// pure functions of the launch shape, so the result is bit-identical run to run.
+__device__ __forceinline__ void fused_stats_finish(const FwdParams& p, int lane, int warp) {
+  __shared__ double s_red[3][kFwdWarps];
+  // The sums are formed HERE, from the mean depths this warp stored a moment ago (its own writes, L1/L2-hot), and not
+  // inside the tile loop: fp64 accumulators that live across the gather loop cost registers exactly where the loop needs
+  // them for loads in flight.
+  double s = 0.0, s2 = 0.0, c = 0.0;
+  for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
+       tile += (int64_t)gridDim.x * kFwdWarps) {
+    const int64_t n = tile * p.tv + lane;
+    if (lane < p.tv && n < p.N) {
+      const float zb = p.zbar[n];
+      if (p.bidx[n] >= 0 && zb > 0.0f) { s += (double)zb; s2 += (double)zb * (double)zb; c += 1.0; }
+    }
+  }
+  s = warp_sum(s); s2 = warp_sum(s2); c = warp_sum(c);
+  if (lane == 0) { s_red[0][warp] = s; s_red[1][warp] = s2; s_red[2][warp] = c; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double a = 0.0, a2 = 0.0, ac = 0.0;
+    for (int w = 0; w < kFwdWarps; ++w) { a += s_red[0][w]; a2 += s_red[1][w]; ac += s_red[2][w]; }
+    double* q = p.partial + (size_t)blockIdx.x * 3;
+    q[0] = a; q[1] = a2; q[2] = ac;
+  }
+}
+
+// Fold of the per-CTA triples by one whole CTA of kScanThreads threads: thread t takes triples t, t+256, ... (loads
+// batched four deep), one shuffle tree per warp, the warps in order.  A pure function of `nparts`: every CTA that
+// calls it gets the same bits.  Result valid in every thread.
+__device__ __forceinline__ void fold_partials(const double* __restrict__ partial, int nparts, double& s, double& s2,
+                                              double& c) {
+  __shared__ double f_red[3][kScanThreads / 32];
+  __shared__ double f_out[3];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double a = 0.0, a2 = 0.0, ac = 0.0;
+  for (int k0 = tid; k0 < nparts; k0 += 4 * kScanThreads) {
+    double v[4][3];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j * kScanThreads;
+      const bool on = k < nparts;
+      const double* q = partial + (size_t)(on ? k : 0) * 3;
+      v[j][0] = on ? __ldcg(q) : 0.0; v[j][1] = on ? __ldcg(q + 1) : 0.0; v[j][2] = on ? __ldcg(q + 2) : 0.0;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { a += v[j][0]; a2 += v[j][1]; ac += v[j][2]; }
+  }
+  a = warp_sum(a); a2 = warp_sum(a2); ac = warp_sum(ac);
+  if (lane == 0) { f_red[0][warp] = a; f_red[1][warp] = a2; f_red[2][warp] = ac; }
+  __syncthreads();
+  if (tid == 0) {
+    a = 0.0; a2 = 0.0; ac = 0.0;
+    for (int w = 0; w < kScanThreads / 32; ++w) { a += f_red[0][w]; a2 += f_red[1][w]; ac += f_red[2][w]; }
+    f_out[0] = a; f_out[1] = a2; f_out[2] = ac;
+  }
+  __syncthreads();
+  s = f_out[0]; s2 = f_out[1]; c = f_out[2];
+}
+
 template <int KIND, int G, int R>
 __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams p) {
   pdl_enter();
@@ -110,7 +200,6 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
   float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
   float* rec_fy = rec_fx + p.vchunk * 32;
   const float4* __restrict__ feats4 = reinterpret_cast<const float4*>(p.feats);
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.counter = 0u;
 
   for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
        tile += (int64_t)gridDim.x * kFwdWarps) {
@@ -217,6 +306,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
       __syncwarp();
     }
   }
+  if (p.fuse_stats) fused_stats_finish(p, lane, warp);
 }
 
 // Any channel count up to 256: the warp takes one voxel at a time, lanes stride over channels (scalar loads).
@@ -232,7 +322,6 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const Fw
   int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
   float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
   float* rec_fy = rec_fx + p.vchunk * 32;
-  if (blockIdx.x == 0 && threadIdx.x == 0) *p.counter = 0u;
 
   for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
        tile += (int64_t)gridDim.x * kFwdWarps) {
@@ -315,6 +404,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const Fw
       __syncwarp();
     }
   }
+  if (p.fuse_stats) fused_stats_finish(p, lane, warp);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -341,26 +431,6 @@ struct StatsParams {
   double* sums;     // (B, 3) Sz, Sz2, n+ of this call's voxels, or NULL (voxel-range sharding: all-reduced by the caller)
   int finalize;     // 1: derive stats from this call's sums alone (unsharded)
 };
-
-// mean / sd of back_project.py:77-78 from the three fp64 sums
-__device__ __forceinline__ void stats_from_sums(double s, double s2, double c, float& mean, float& sd) {
-  if (c > 0.0) {
-    mean = (float)(s / c);
-    const double m = (double)mean;
-    double ssq = s2 - 2.0 * m * s + c * m * m;
-    if (ssq < 0.0) ssq = 0.0;
-    sd = __fadd_rn((float)sqrt(ssq), 1e-5f);
-  } else {
-    mean = __int_as_float(0x7fc00000);  // mean of an empty set is NaN in the reference; never used (z<=0 -> 0)
-    sd = 1e-5f;
-  }
-}
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(kFull, v, o);
-  return v;
-}
 
 __global__ void __launch_bounds__(kStatsThreads) bp_stats_kernel(const StatsParams p) {
   pdl_enter();
@@ -445,6 +515,7 @@ __global__ void __launch_bounds__(kStatsThreads) bp_stats_kernel(const StatsPara
       p.stats[2 * b + 1] = sd;
     }
   }
+  if (tid == 0) *p.counter = 0u;  // ready for the next user of the ticket
 }
 
 // voxel-range sharding: stats from the all-reduced sums of every shard
@@ -458,17 +529,98 @@ __global__ void bp_stats_from_sums_kernel(const double* __restrict__ sums, float
   stats[2 * b + 1] = sd;
 }
 
-__global__ void __launch_bounds__(256) bp_normalise_kernel(const float* __restrict__ zbar, const int* __restrict__ bidx,
-                                                           const float* __restrict__ stats, float* __restrict__ out,
-                                                           int64_t N, int C1) {
+// ------------------------------------------------------------------------------------------------
+// bp_fwd_finish: ONE launch for the two independent jobs that follow the gather --
+//   CTAs [0, scan_ctas)  exclusive scan of the bin histogram the gather just produced (first step of the backward
+//                        pass: it needs nothing but the histogram, so it runs here instead of opening the backward chain);
+//   the other CTAs       depth normalisation back_project.py:79-80: out[n, C] = (z - mu) / sd, 0 where z <= 0.
+// Either job may be absent (no histogram wanted / sharded call whose statistics are not final yet).
+// ------------------------------------------------------------------------------------------------
+struct FinishParams {
+  BinState bins;
+  int scan_ctas;
+  int sums_ctas;          // 1: one extra CTA folds the per-CTA triples into `sums` (voxel-range sharding), else 0
+  const double* partial;  // per-CTA triples of the gather launch (single-fragment calls), or NULL
+  int nparts;             // number of triples; 0 -> `stats` was written by bp_stats_kernel / bp_stats_from_sums_kernel
+  double* sums;
+  const float* zbar;
+  const int* bidx;
+  const float* stats;
+  float* out;
+  int64_t N;
+  int C1;
+};
+
+__global__ void __launch_bounds__(kScanThreads) bp_fwd_finish_kernel(const FinishParams p) {
   pdl_enter();
-  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= N) return;
-  const int b = bidx[n];
-  const float z = zbar[n];
+  int i = blockIdx.x;
+  if (i < p.scan_ctas) {
+    scan_bins_cta(p.bins);
+    return;
+  }
+  i -= p.scan_ctas;
+  if (i < p.sums_ctas) {
+    double s, s2, c;
+    fold_partials(p.partial, p.nparts, s, s2, c);
+    if (threadIdx.x == 0) { p.sums[0] = s; p.sums[1] = s2; p.sums[2] = c; }
+    return;
+  }
+  i -= p.sums_ctas;
+  float mean0 = 0.0f, sd0 = 1.0f;
+  if (p.nparts > 0) {  // single fragment: statistics from the gather's per-CTA triples, folded by this CTA for itself
+    double s, s2, c;
+    fold_partials(p.partial, p.nparts, s, s2, c);
+    stats_from_sums(s, s2, c, mean0, sd0);
+  }
+  const int64_t n = (int64_t)i * kScanThreads + threadIdx.x;
+  if (n >= p.N) return;
+  const int b = p.bidx[n];
+  const float z = p.zbar[n];
   float zn = 0.0f;
-  if (b >= 0 && z > 0.0f) zn = __fdiv_rn(__fsub_rn(z, stats[2 * b]), stats[2 * b + 1]);
-  out[n * C1 + (C1 - 1)] = zn;
+  if (b >= 0 && z > 0.0f) {
+    const float mean = p.nparts > 0 ? mean0 : p.stats[2 * b], sd = p.nparts > 0 ? sd0 : p.stats[2 * b + 1];
+    zn = __fdiv_rn(__fsub_rn(z, mean), sd);
+  }
+  p.out[n * p.C1 + (p.C1 - 1)] = zn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// bp_prep: ONE launch in front of the gather --
+//   (n_maps, C, H*W) -> (n_maps, H*W, C) relayout of the feature maps through a padded 32x32 shared-memory tile (both
+//   sides coalesced; skipped when the producer already is channels-last), and
+//   the clear of the binning-state prefix / the statistics ticket (BinLayout), spread over the same CTAs.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) bp_prep_kernel(const float* __restrict__ src, float* __restrict__ dst, int A, int Bn,
+                                                      uint32_t* __restrict__ zero_ptr, int64_t zero_words) {
+  pdl_enter();
+  __shared__ float tile[32][33];
+  if (zero_words > 0) {
+    const int64_t ctas = (int64_t)gridDim.x * gridDim.y * gridDim.z;
+    const int64_t cta = ((int64_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    const int64_t nv = zero_words >> 2;                       // whole uint4s; the tail words go to CTA 0
+    const int64_t per = (nv + ctas - 1) / ctas;
+    const int64_t v0 = cta * per, v1 = min(nv, v0 + per);
+    uint4* v = reinterpret_cast<uint4*>(zero_ptr);
+    for (int64_t i = v0 + threadIdx.x; i < v1; i += 256) v[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (cta == 0 && threadIdx.x < (int)(zero_words & 3)) zero_ptr[(nv << 2) + threadIdx.x] = 0u;
+  }
+  if (src == nullptr) return;
+  const int64_t map = blockIdx.z;
+  const float* s = src + map * (int64_t)A * Bn;
+  float* d = dst + map * (int64_t)A * Bn;
+  const int b0 = blockIdx.x * 32, a0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int a = a0 + ty + i, b = b0 + tx;
+    if (a < A && b < Bn) tile[ty + i][tx] = __ldg(s + (int64_t)a * Bn + b);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 32; i += 8) {
+    const int b = b0 + ty + i, a = a0 + tx;
+    if (a < A && b < Bn) d[(int64_t)b * A + a] = tile[tx][ty + i];
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -479,6 +631,10 @@ struct FwdWs {
   int nchunks;
   int64_t chunk;
 };
+
+constexpr int kFwdMaxCtasPerSm = 32;
+constexpr int kFuseStatsMaxCtas = 1024;
+constexpr int kFwdMaxSms = 256;  // bound of the per-warp partial table (a B200 has 148 SMs)
 
 static FwdWs fwd_ws_layout(int64_t N, int B) {
   FwdWs w;
@@ -492,10 +648,14 @@ static FwdWs fwd_ws_layout(int64_t N, int B) {
   }
   w.nchunks = (int)nch;
   w.chunk = chunk;
+  // partial table: B > 1 -> (nchunks, B, 3) of the stats kernel; B == 1 -> one triple per CTA of the gather launch
+  size_t part = sizeof(double) * 3 * (size_t)nch * (size_t)(B > 0 ? B : 1);
+  const size_t fused = sizeof(double) * 3 * (size_t)kFuseStatsMaxCtas;
+  if (B == 1 && fused > part) part = fused;
   size_t o = 0;
   w.zbar = o; o = align_up(o + sizeof(float) * (size_t)(N > 0 ? N : 1), 256);
   w.bidx = o; o = align_up(o + sizeof(int) * (size_t)(N > 0 ? N : 1), 256);
-  w.partial = o; o = align_up(o + sizeof(double) * 3 * (size_t)nch * (size_t)(B > 0 ? B : 1), 256);
+  w.partial = o; o = align_up(o + part, 256);
   w.stats = o; o = align_up(o + sizeof(float) * 2 * (size_t)(B > 0 ? B : 1), 256);
   w.counter = o; o = align_up(o + 256, 256);
   w.total = o;
@@ -546,7 +706,7 @@ static int env_int(const char* name, int dflt) {
 }
 
 template <int KIND>
-static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
+static int launch_fwd(const FwdParams& p0, cudaStream_t stream, int* grid_out, int* fused_out) {
   FwdParams p = p0;
   int G, R;
   fwd_kernel_t k = pick_fwd_kernel<KIND>(p.C, G, R);
@@ -558,6 +718,7 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (sms > kFwdMaxSms) sms = kFwdMaxSms;
   // Launch shape.  Large N: 32-voxel warp tiles, grid capped at 32 CTAs per SM (grid-stride).  Small N (the launch is a
   // single wave): the kernel's duration is ONE warp's chain -- views x projection, then tile/NG rounds of count[n] dependent
   // gather steps -- so the tile shrinks, down to D3M_FWD_TVMIN voxels (a multiple of 4 keeps the bulk store 16-byte
@@ -581,14 +742,45 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream) {
   D3M_REQUIRE(smem <= 200 * 1024, D3M_ERR_ARG, "back_project: C=%d needs %zu B shared memory per CTA", p.C, smem);
   D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t ctas = (p.num_tiles + kFwdWarps - 1) / kFwdWarps;
-  const int64_t cap = (int64_t)sms * 32;
+  const int64_t cap = (int64_t)sms * kFwdMaxCtasPerSm;
   if (ctas > cap) ctas = cap;
   if (ctas < 1) ctas = 1;
+  // Fused statistics only for launches of up to kFuseStatsMaxCtas CTAs: every CTA of bp_fwd_finish folds the per-CTA
+  // triples for itself, which is free for a fragment (a few hundred triples from L2) and a 400 MB re-read at dense 96^3
+  // (4736 triples x 3456 CTAs: bp_fwd_finish 62 us instead of 21).  Larger launches keep the separate stats kernel.
+  if (ctas > kFuseStatsMaxCtas) p.fuse_stats = 0;
+  *fused_out = p.fuse_stats;
+  *grid_out = (int)ctas;
   {
     LaunchScope ls("bp_fwd", stream);
     launch_k(k, dim3((unsigned)ctas), dim3(kFwdWarps * 32), smem, stream, p);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
+  return D3M_OK;
+}
+
+// relayout and / or clear in front of the gather (one launch; none when there is nothing to do)
+static int launch_prep(const float* src_nchw, float* dst_nhwc, int64_t n_maps, int C, int HW, uint32_t* zero_ptr,
+                       int64_t zero_words, cudaStream_t stream) {
+  if (src_nchw == nullptr) {
+    if (zero_words == 0) return D3M_OK;
+    int64_t ctas = ((zero_words >> 2) + 255) / 256;
+    if (ctas > 148 * 8) ctas = 148 * 8;
+    if (ctas < 1) ctas = 1;
+    LaunchScope ls("bp_prep", stream);
+    launch_k(bp_prep_kernel, dim3((unsigned)ctas), dim3(256), 0, stream, (const float*)nullptr, (float*)nullptr, 0, 0,
+             zero_ptr, zero_words);
+    D3M_CUDA_CHECK(cudaGetLastError());
+    return D3M_OK;
+  }
+  for (int64_t m0 = 0; m0 < n_maps; m0 += 65535) {
+    const unsigned nz = (unsigned)((n_maps - m0) < 65535 ? (n_maps - m0) : 65535);
+    dim3 grid((HW + 31) / 32, (C + 31) / 32, nz);
+    LaunchScope ls("bp_prep", stream);
+    launch_k(bp_prep_kernel, grid, dim3(256), 0, stream, src_nchw + m0 * (int64_t)C * HW, dst_nhwc + m0 * (int64_t)C * HW, C,
+             HW, zero_ptr, m0 == 0 ? zero_words : (int64_t)0);
+    D3M_CUDA_CHECK(cudaGetLastError());
+  }
   return D3M_OK;
 }
 
@@ -598,8 +790,7 @@ using namespace d3m;
 
 extern "C" size_t d3m_back_project_cell_hist_elems(int64_t N, int B, int V, int H, int W) {
   if (N < 0 || B < 1 || V < 1 || H < 1 || W < 1) return 0;
-  const int64_t M = (int64_t)V * B * H * W;
-  return (size_t)(M << bin_config(N, V, M).nb_log2);
+  return bin_layout(N, B, V, H, W).total;
 }
 
 extern "C" size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C) {
@@ -608,18 +799,22 @@ extern "C" size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C)
   return fwd_ws_layout(N, B).total;
 }
 
-static int fwd_check(const void* coords, int coords_kind, int64_t N, const float* origin, int B, const float* feats_nhwc,
-                     int V, int C, int H, int W, const float* KRcam, float* out, float* count, void* workspace,
-                     size_t workspace_bytes) {
+static int fwd_check(const void* coords, int coords_kind, int64_t N, const float* origin, int B, const float* feats,
+                     int feats_layout, const float* scratch, int V, int C, int H, int W, const float* KRcam, float* out,
+                     float* count, void* workspace, size_t workspace_bytes) {
   D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "back_project: no CUDA device (there is no CPU fallback)");
   D3M_REQUIRE(N >= 0 && B >= 1 && V >= 1 && C >= 1 && H >= 2 && W >= 2, D3M_ERR_ARG,
               "back_project: bad sizes N=%lld B=%d V=%d C=%d H=%d W=%d", (long long)N, B, V, C, H, W);
   D3M_REQUIRE(coords_kind >= 0 && coords_kind <= 2, D3M_ERR_ARG, "back_project: coords_kind=%d", coords_kind);
+  D3M_REQUIRE(feats_layout == D3M_FEATS_NHWC || feats_layout == D3M_FEATS_NCHW, D3M_ERR_ARG,
+              "back_project: feats_layout=%d", feats_layout);
   D3M_REQUIRE((int64_t)V * B * H * W < (1ll << 30), D3M_ERR_ARG, "back_project: V*B*H*W must be < 2^30 texels");
   if (N == 0) return D3M_OK;
-  D3M_REQUIRE(coords && origin && feats_nhwc && KRcam && out && count && workspace, D3M_ERR_ARG,
+  D3M_REQUIRE(coords && origin && feats && KRcam && out && count && workspace, D3M_ERR_ARG,
               "back_project: NULL pointer");
-  D3M_REQUIRE(aligned16(coords) && aligned16(feats_nhwc) && aligned16(KRcam) && aligned16(out) &&
+  D3M_REQUIRE(feats_layout == D3M_FEATS_NHWC || scratch, D3M_ERR_ARG,
+              "back_project: (V,B,C,H,W) feats need the channels-last scratch buffer");
+  D3M_REQUIRE(aligned16(coords) && aligned16(feats) && aligned16(scratch) && aligned16(KRcam) && aligned16(out) &&
                   aligned16(workspace),
               D3M_ERR_ALIGN, "back_project: coords/feats/KRcam/out/workspace must be 16-byte aligned");
   const FwdWs w = fwd_ws_layout(N, B);
@@ -628,81 +823,125 @@ static int fwd_check(const void* coords, int coords_kind, int64_t N, const float
   return D3M_OK;
 }
 
-static int fwd_normalise(int64_t N, int C, const FwdWs& w, unsigned char* ws, float* out, cudaStream_t stream) {
-  LaunchScope ls("bp_fwd_normalise", stream);
-  launch_k(bp_normalise_kernel, dim3((unsigned)((N + 255) / 256)), dim3(256), 0, stream, 
-      reinterpret_cast<const float*>(ws + w.zbar), reinterpret_cast<const int*>(ws + w.bidx),
-      reinterpret_cast<const float*>(ws + w.stats), out, N, C + 1);
+// scan of the fresh histogram and / or depth normalisation (and / or the fold of the statistics triples into `sums` for
+// the sharded caller), one launch (none when nothing is due)
+static int fwd_finish_launch(int64_t N, int C, const FwdWs& w, unsigned char* ws, float* out, int* cell_hist,
+                             const BinLayout* bl, bool normalise, int nparts, double* sums, cudaStream_t stream) {
+  FinishParams fp;
+  memset(&fp, 0, sizeof(fp));
+  if (cell_hist) {
+    fp.bins = bin_state(cell_hist, *bl);
+    fp.scan_ctas = bl->nchunks;
+  }
+  fp.partial = reinterpret_cast<const double*>(ws + w.partial);
+  fp.nparts = nparts;
+  fp.sums = sums;
+  fp.sums_ctas = (sums && nparts > 0) ? 1 : 0;
+  fp.zbar = reinterpret_cast<const float*>(ws + w.zbar);
+  fp.bidx = reinterpret_cast<const int*>(ws + w.bidx);
+  fp.stats = reinterpret_cast<const float*>(ws + w.stats);
+  fp.out = out; fp.N = normalise ? N : 0; fp.C1 = C + 1;
+  const int64_t norm_ctas = normalise ? (N + kScanThreads - 1) / kScanThreads : 0;
+  const int64_t ctas = fp.scan_ctas + fp.sums_ctas + norm_ctas;
+  if (ctas == 0) return D3M_OK;
+  LaunchScope ls("bp_fwd_finish", stream);
+  launch_k(bp_fwd_finish_kernel, dim3((unsigned)ctas), dim3(kScanThreads), 0, stream, fp);
   D3M_CUDA_CHECK(cudaGetLastError());
   return D3M_OK;
 }
 
-// gather + per-fragment depth sums; `depth_sums` != NULL -> sharded mode: sums are handed to the caller and the depth
-// channel is left un-normalised until d3m_back_project_fwd_finish.
+// relayout/clear + gather + per-fragment depth sums (+ scan of the histogram, + normalisation);
+// `depth_sums` != NULL -> sharded mode: sums are handed to the caller and the depth channel is left un-normalised
+// until d3m_back_project_fwd_finish.
 static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float* origin, int B, float voxel_size,
-                    const float* feats_nhwc, int V, int C, int H, int W, const float* KRcam, float* out, float* count,
-                    int* cell_hist, void* workspace, size_t workspace_bytes, double* depth_sums, cudaStream_t stream) {
-  int rc = fwd_check(coords, coords_kind, N, origin, B, feats_nhwc, V, C, H, W, KRcam, out, count, workspace,
-                     workspace_bytes);
+                    const float* feats, int feats_layout, float* feats_nhwc_scratch, int V, int C, int H, int W,
+                    const float* KRcam, float* out, float* count, int* cell_hist, void* workspace, size_t workspace_bytes,
+                    double* depth_sums, cudaStream_t stream) {
+  int rc = fwd_check(coords, coords_kind, N, origin, B, feats, feats_layout, feats_nhwc_scratch, V, C, H, W, KRcam, out,
+                     count, workspace, workspace_bytes);
   if (rc != D3M_OK) return rc;
+  BinLayout bl;
+  memset(&bl, 0, sizeof(bl));
   if (cell_hist) {
     D3M_REQUIRE(aligned16(cell_hist), D3M_ERR_ALIGN, "back_project: cell_hist must be 16-byte aligned");
-    rc = zero_async(cell_hist, sizeof(int) * d3m_back_project_cell_hist_elems(N, B, V, H, W), stream);
-    if (rc != D3M_OK) return rc;
+    bl = bin_layout(N, B, V, H, W);
   }
   if (N == 0) {
+    if (cell_hist) D3M_CUDA_CHECK(cudaMemsetAsync(cell_hist, 0, sizeof(int) * bl.total, stream));  // empty bins, start = 0
     if (depth_sums) D3M_CUDA_CHECK(cudaMemsetAsync(depth_sums, 0, sizeof(double) * 3 * (size_t)B, stream));
     return D3M_OK;
   }
   const FwdWs w = fwd_ws_layout(N, B);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
+  // the statistics ticket lives in the binning state when there is one (cleared together with it), else in the workspace
+  unsigned int* ticket = cell_hist ? bin_state(cell_hist, bl).counters + kCtrStatsTicket
+                                   : reinterpret_cast<unsigned int*>(ws + w.counter);
+  uint32_t* zero_ptr = cell_hist ? reinterpret_cast<uint32_t*>(cell_hist) : reinterpret_cast<uint32_t*>(ws + w.counter);
+  // without a binning state only the stats kernel's ticket needs clearing; a single small fragment (fused statistics)
+  // does not use it, and is the one case where the clear would be a launch of its own
+  const bool maybe_fused = B == 1 && (N + 3) / 4 / kFwdWarps <= kFuseStatsMaxCtas;
+  const int64_t zero_words = cell_hist ? (int64_t)bl.zero_elems : (maybe_fused ? 0 : 4);
+  const float* feats_nhwc = feats;
+  if (feats_layout == D3M_FEATS_NCHW) {
+    rc = launch_prep(feats, feats_nhwc_scratch, (int64_t)V * B, C, H * W, zero_ptr, zero_words, stream);
+    feats_nhwc = feats_nhwc_scratch;
+  } else {
+    rc = launch_prep(nullptr, nullptr, 0, 0, 0, zero_ptr, zero_words, stream);
+  }
+  if (rc != D3M_OK) return rc;
   FwdParams p;
+  memset(&p, 0, sizeof(p));
   p.coords = coords; p.N = N; p.origin = origin; p.B = B; p.vs = voxel_size;
   p.feats = feats_nhwc; p.V = V; p.C = C; p.H = H; p.W = W; p.KR = KRcam;
-  p.out = out; p.count = count; p.cell_hist = cell_hist;
-  {
-    const BinCfg bc = bin_config(N, V, (int64_t)V * B * H * W);
-    p.nb_log2 = bc.nb_log2;
-  }
+  p.out = out; p.count = count;
+  p.cell_hist = cell_hist ? cell_hist + bl.cnt : nullptr;
+  p.nb_log2 = cell_hist ? bl.nb_log2 : 0;
   p.zbar = reinterpret_cast<float*>(ws + w.zbar);
   p.bidx = reinterpret_cast<int*>(ws + w.bidx);
-  p.counter = reinterpret_cast<unsigned int*>(ws + w.counter);
-  if (coords_kind == D3M_COORDS_F32) rc = launch_fwd<D3M_COORDS_F32>(p, stream);
-  else if (coords_kind == D3M_COORDS_I64) rc = launch_fwd<D3M_COORDS_I64>(p, stream);
-  else rc = launch_fwd<D3M_COORDS_I32>(p, stream);
+  p.counter = ticket;
+  p.fuse_stats = (B == 1) ? 1 : 0;
+  p.partial = reinterpret_cast<double*>(ws + w.partial);
+  p.stats = reinterpret_cast<float*>(ws + w.stats);
+  p.sums = depth_sums;
+  p.finalize = depth_sums ? 0 : 1;
+  int fwd_grid = 0, fused = 0;
+  if (coords_kind == D3M_COORDS_F32) rc = launch_fwd<D3M_COORDS_F32>(p, stream, &fwd_grid, &fused);
+  else if (coords_kind == D3M_COORDS_I64) rc = launch_fwd<D3M_COORDS_I64>(p, stream, &fwd_grid, &fused);
+  else rc = launch_fwd<D3M_COORDS_I32>(p, stream, &fwd_grid, &fused);
+  p.fuse_stats = fused;
   if (rc != D3M_OK) return rc;
-  StatsParams sp;
-  sp.zbar = p.zbar; sp.bidx = p.bidx; sp.N = N; sp.B = B; sp.nchunks = w.nchunks; sp.chunk = w.chunk;
-  sp.partial = reinterpret_cast<double*>(ws + w.partial);
-  sp.stats = reinterpret_cast<float*>(ws + w.stats);
-  sp.counter = p.counter;
-  sp.sums = depth_sums;
-  sp.finalize = depth_sums ? 0 : 1;
-  {
+  if (!p.fuse_stats) {
+    StatsParams sp;
+    sp.zbar = p.zbar; sp.bidx = p.bidx; sp.N = N; sp.B = B; sp.nchunks = w.nchunks; sp.chunk = w.chunk;
+    sp.partial = p.partial;
+    sp.stats = p.stats;
+    sp.counter = ticket;
+    sp.sums = depth_sums;
+    sp.finalize = depth_sums ? 0 : 1;
     LaunchScope ls("bp_fwd_stats", stream);
     launch_k(bp_stats_kernel, dim3(w.nchunks), dim3(kStatsThreads), 0, stream, sp);
+    D3M_CUDA_CHECK(cudaGetLastError());
   }
-  D3M_CUDA_CHECK(cudaGetLastError());
-  if (depth_sums) return D3M_OK;
-  return fwd_normalise(N, C, w, ws, out, stream);
+  return fwd_finish_launch(N, C, w, ws, out, cell_hist, &bl, depth_sums == nullptr, p.fuse_stats ? fwd_grid : 0,
+                           p.fuse_stats ? depth_sums : nullptr, stream);
 }
 
 extern "C" int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
-                                    float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                                    const float* KRcam, float* out, float* count, int* cell_hist, void* workspace,
-                                    size_t workspace_bytes, void* stream_) {
-  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats_nhwc, V, C, H, W, KRcam, out, count, cell_hist,
-                  workspace, workspace_bytes, nullptr, static_cast<cudaStream_t>(stream_));
+                                    float voxel_size, const float* feats, int feats_layout, float* feats_nhwc_scratch,
+                                    int V, int C, int H, int W, const float* KRcam, float* out, float* count,
+                                    int* cell_hist, void* workspace, size_t workspace_bytes, void* stream_) {
+  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats, feats_layout, feats_nhwc_scratch, V, C, H, W,
+                  KRcam, out, count, cell_hist, workspace, workspace_bytes, nullptr, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int d3m_back_project_fwd_partial(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
-                                            float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                                            const float* KRcam, float* out, float* count, int* cell_hist,
-                                            double* depth_sums, void* workspace, size_t workspace_bytes,
-                                            void* stream_) {
+                                            float voxel_size, const float* feats, int feats_layout,
+                                            float* feats_nhwc_scratch, int V, int C, int H, int W, const float* KRcam,
+                                            float* out, float* count, int* cell_hist, double* depth_sums,
+                                            void* workspace, size_t workspace_bytes, void* stream_) {
   D3M_REQUIRE(depth_sums, D3M_ERR_ARG, "back_project_fwd_partial: NULL depth_sums");
-  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats_nhwc, V, C, H, W, KRcam, out, count, cell_hist,
-                  workspace, workspace_bytes, depth_sums, static_cast<cudaStream_t>(stream_));
+  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats, feats_layout, feats_nhwc_scratch, V, C, H, W,
+                  KRcam, out, count, cell_hist, workspace, workspace_bytes, depth_sums, static_cast<cudaStream_t>(stream_));
 }
 
 extern "C" int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sums, float* out,
@@ -721,5 +960,5 @@ extern "C" int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double
     launch_k(bp_stats_from_sums_kernel, dim3((B + 127) / 128), dim3(128), 0, stream, depth_sums, reinterpret_cast<float*>(ws + w.stats), B);
   }
   D3M_CUDA_CHECK(cudaGetLastError());
-  return fwd_normalise(N, C, w, ws, out, stream);
+  return fwd_finish_launch(N, C, w, ws, out, nullptr, nullptr, true, 0, nullptr, stream);
 }

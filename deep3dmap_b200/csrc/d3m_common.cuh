@@ -113,6 +113,164 @@ static inline BinCfg bin_config(int64_t N, int V, int64_t M) {
   while (c.nb_log2 < 6 && per_cell > 32.0 * (double)(1 << c.nb_log2) && (M << (c.nb_log2 + 1)) < (1ll << 30)) ++c.nb_log2;
   return c;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Binning state: ONE int32 buffer that travels from the forward call to the backward call (the `cell_hist` argument of
+// the C ABI) or lives in the backward workspace when forward did not produce it.  Offsets in int32 elements, every
+// section 16-byte aligned:
+//   [cnt      Mb      ]  samples per bin, integer RED in bp_fwd (or bp_bwd_hist)            zeroed by the prep kernel
+//   [cursor   Mb      ]  claim counters of the fill pass; gather re-zeroes every cell it owns  (self-cleaning)
+//   [scan_st  2*nchunks]  decoupled-look-back words; the last scan CTA re-zeroes them          (self-cleaning)
+//   [counters 16      ]  0: scan ticket, 1: scan done, 2: forward stats ticket                (self-cleaning)
+//   ---------------------  zero_elems: the prefix the prep kernel clears ONCE per forward call
+//   [start    Mb+1    ]  exclusive scan of cnt (written by the scan CTAs of bp_fwd_finish)
+// Because cursor / scan state / counters clean up after themselves, backward may run any number of times on the state of
+// one forward call without another clear, and no launch of the fragment step exists only to zero memory.
+// ------------------------------------------------------------------------------------------------
+constexpr int kScanThreads = 256;
+constexpr int kScanItems = 8;
+constexpr int kScanChunk = kScanThreads * kScanItems;
+enum { kCtrScanTicket = 0, kCtrScanDone = 1, kCtrStatsTicket = 2, kCtrCount = 16 };
+
+struct BinLayout {
+  int64_t M, Mb;
+  int nb_log2, nchunks;
+  size_t cnt, cursor, scan_state, counters, zero_elems, start, total;  // int32 element offsets
+};
+static inline size_t align4(size_t x) { return (x + 3) & ~(size_t)3; }
+static inline BinLayout bin_layout(int64_t N, int B, int V, int H, int W) {
+  BinLayout l;
+  l.M = (int64_t)V * B * H * W;
+  l.nb_log2 = bin_config(N, V, l.M).nb_log2;
+  l.Mb = l.M << l.nb_log2;
+  l.nchunks = (int)((l.Mb + kScanChunk - 1) / kScanChunk);
+  size_t o = 0;
+  l.cnt = o; o = align4(o + (size_t)l.Mb);
+  l.cursor = o; o = align4(o + (size_t)l.Mb);
+  l.scan_state = o; o = align4(o + 2 * (size_t)l.nchunks);
+  l.counters = o; o = align4(o + kCtrCount);
+  l.zero_elems = o;
+  l.start = o; o = align4(o + (size_t)l.Mb + 1);
+  l.total = o;
+  return l;
+}
+
+// Device view of the binning state.
+struct BinState {
+  int* cnt;
+  int* cursor;
+  int* start;                      // Mb + 1
+  unsigned long long* scan_state;  // nchunks
+  unsigned int* counters;
+  int64_t Mb;
+  int nb_log2, nchunks;
+};
+static inline BinState bin_state(int* base, const BinLayout& l) {
+  BinState s;
+  s.cnt = base + l.cnt; s.cursor = base + l.cursor; s.start = base + l.start;
+  s.scan_state = reinterpret_cast<unsigned long long*>(base + l.scan_state);
+  s.counters = reinterpret_cast<unsigned int*>(base + l.counters);
+  s.Mb = l.Mb; s.nb_log2 = l.nb_log2; s.nchunks = l.nchunks;
+  return s;
+}
+
+// ---- exclusive scan of the bin histogram: ONE pass, chained look-back ---------------------------------------------
+// Executed by a whole CTA of kScanThreads threads for ONE chunk.  CTAs take chunk ids from a ticket (so a chunk's
+// predecessors are always already scheduled), publish their aggregate, walk back over predecessors until they meet an
+// inclusive prefix, then publish their own.  state word = (flag << 32) | value, flag 0 = not ready, 1 = aggregate,
+// 2 = inclusive prefix.  Integer sums: the result does not depend on the order in which CTAs arrive.  The last CTA to
+// finish clears the look-back words and both counters again (see BinLayout).
+__device__ __forceinline__ void scan_bins_cta(const BinState& st) {
+  __shared__ int red[kScanThreads / 32];
+  __shared__ int s_cid, s_prefix;
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_cid = (int)atomicAdd(&st.counters[kCtrScanTicket], 1u);
+  __syncthreads();
+  const int cid = s_cid;
+  const int64_t base = (int64_t)cid * kScanChunk + (int64_t)tid * kScanItems;
+  int v[kScanItems];
+  if (base + kScanItems <= st.Mb) {
+    const int4* q = reinterpret_cast<const int4*>(st.cnt + base);
+#pragma unroll
+    for (int i = 0; i < kScanItems / 4; ++i) {
+      const int4 t = __ldcg(q + i);
+      v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < kScanItems; ++i) v[i] = (base + i < st.Mb) ? __ldcg(st.cnt + base + i) : 0;
+  }
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) s += v[i];
+  int inc = s;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += t;
+  }
+  if (lane == 31) red[warp] = inc;
+  __syncthreads();
+  int woff = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < kScanThreads / 32; ++w) {
+    if (w < warp) woff += red[w];
+    total += red[w];
+  }
+  if (warp == 0) {
+    // decoupled look-back, one warp wide: lane l inspects chunk cid-1-l; the nearest predecessor that already holds an
+    // inclusive prefix (state 2) ends the walk, the aggregates (state 1) in front of it are summed with one shuffle tree.
+    volatile unsigned long long* sw = st.scan_state;
+    int prefix = 0;
+    if (cid == 0) {
+      if (lane == 0) sw[0] = (2ull << 32) | (unsigned)total;
+    } else {
+      if (lane == 0) {
+        sw[cid] = (1ull << 32) | (unsigned)total;
+        __threadfence();
+      }
+      for (int j0 = cid - 1;; j0 -= 32) {
+        const int j = j0 - lane;
+        unsigned long long w = 2ull << 32;  // "chunk -1": inclusive prefix 0
+        if (j >= 0) {
+          do { w = sw[j]; } while ((w >> 32) == 0ull);
+        }
+        const unsigned done = __ballot_sync(0xffffffffu, (w >> 32) == 2ull);
+        const int first = __ffs(done) - 1;  // -1: no inclusive prefix in this window
+        int use = (done == 0u || lane <= first) ? (int)(unsigned)(w & 0xffffffffull) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) use += __shfl_xor_sync(0xffffffffu, use, o);
+        prefix += use;
+        if (done != 0u) break;
+      }
+      if (lane == 0) sw[cid] = (2ull << 32) | (unsigned)(prefix + total);
+    }
+    if (lane == 0) {
+      s_prefix = prefix;
+      if (cid == st.nchunks - 1) st.start[st.Mb] = prefix + total;
+    }
+  }
+  __syncthreads();
+  int off = s_prefix + woff + inc - s;
+#pragma unroll
+  for (int i = 0; i < kScanItems; ++i) {
+    if (base + i < st.Mb) st.start[base + i] = off;
+    off += v[i];
+  }
+  // self-cleaning: once every chunk has finished its look-back nobody reads the state words any more
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    s_last = atomicAdd(&st.counters[kCtrScanDone], 1u) == (unsigned)(st.nchunks - 1);
+  }
+  __syncthreads();
+  if (s_last) {
+    for (int i = tid; i < st.nchunks; i += kScanThreads) st.scan_state[i] = 0ull;
+    if (tid == 0) { st.counters[kCtrScanTicket] = 0u; st.counters[kCtrScanDone] = 0u; }
+  }
+}
+
 __host__ __device__ static inline int align_up_dev(int x) { return (x + 15) & ~15; }
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 

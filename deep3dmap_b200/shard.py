@@ -127,8 +127,10 @@ class _CudaLocalOps:
             raise _lib.D3MError("back_project_voxel_sharded: feats must live on a CUDA device (no CPU fallback)")
         dev = feats.device
         coords, origin, KRcam = voxel._prep_small(coords, origin, KRcam, dev)
-        nhwc = voxel.feats_to_channels_last(feats.float())
-        V, B, H, W, C = nhwc.shape
+        store, layout = voxel._feats_layout(feats.float())
+        V, B, C, H, W = feats.shape
+        scratch = (torch.empty((V, B, H, W, C), dtype=torch.float32, device=dev)
+                   if layout == _lib.FEATS_NCHW and coords.shape[0] > 0 else None)
         N = coords.shape[0]
         out = torch.empty((N, C + 1), dtype=torch.float32, device=dev)
         count = torch.empty((N,), dtype=torch.float32, device=dev)
@@ -140,11 +142,12 @@ class _CudaLocalOps:
         if N > 0:
             with voxel._on_device(dev):
                 rc = L.d3m_back_project_fwd_partial(coords.data_ptr(), voxel._COORD_KIND[coords.dtype], N,
-                                                    origin.data_ptr(), B, float(voxel_size), nhwc.data_ptr(), V, C, H, W,
+                                                    origin.data_ptr(), B, float(voxel_size), store.data_ptr(), layout,
+                                                    voxel._ptr(scratch), V, C, H, W,
                                                     KRcam.data_ptr(), out.data_ptr(), count.data_ptr(), voxel._ptr(hist),
                                                     sums.data_ptr(), ws.data_ptr(), ws_bytes, voxel._stream(dev))
             _lib.check(rc, "d3m_back_project_fwd_partial")
-        return out, count, sums, (ws, ws_bytes, tuple(nhwc.shape), coords, origin, KRcam, hist)
+        return out, count, sums, (ws, ws_bytes, (V, B, H, W, C), coords, origin, KRcam, hist)
 
     @staticmethod
     def forward_finish(out, sums, state):
@@ -171,12 +174,7 @@ class _CudaLocalOps:
         """Backward restricted to views [v0, v1): writes out (v1-v0, B, C, H, W).  A texel's gradient only collects
         samples of its own view, so the slices of consecutive calls are bit-identical to one full call."""
         _, _, (V, B, H, W, C), coords, origin, KRcam, hist = state
-        hs = None
-        if hist is not None and hist.numel() % V == 0:
-            per_view = hist.numel() // V          # (H*W*B) << nb_log2 of the forward call
-            same_bins = _lib.lib().d3m_back_project_cell_hist_elems(coords.shape[0], B, v1 - v0, H, W) == per_view * (v1 - v0)
-            if same_bins and (per_view * v0 * 4) % 16 == 0:
-                hs = hist[per_view * v0: per_view * v1]
+        hs = None   # the binning state of the full call cannot be sliced by view: a range rebuilds its own (3 extra launches)
         return voxel.back_project_backward(coords, origin, voxel_size, (v1 - v0, B, H, W, C), KRcam[v0:v1].contiguous(),
                                            grad_out, nchw=True, count=count, cell_hist=hs, out=out)
 

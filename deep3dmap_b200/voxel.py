@@ -83,7 +83,7 @@ def _memo(key, query):
 
 def _new_cell_hist(N, B, V, H, W, dev):
     n = _memo(("h", N, B, V, H, W), lambda: _lib.lib().d3m_back_project_cell_hist_elems(N, B, V, H, W))
-    return (torch.empty if N > 0 else torch.zeros)((n,), dtype=torch.int32, device=dev)
+    return torch.empty((n,), dtype=torch.int32, device=dev)   # cleared by the library (prep launch)
 
 
 def _workspace(kind, key, dev):
@@ -140,12 +140,27 @@ def _prep_small(coords, origin, KRcam, device):
     return coords, _as(origin, device, torch.float32), _as(KRcam, device, torch.float32)
 
 
-def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam, cell_hist=False):
-    """Kernel-level forward on channels-last maps (V,B,H,W,C).  Returns (volume (N,C+1), count (N,)) and, with
-    cell_hist=True, additionally the int32 per-bin sample histogram the backward pass starts from."""
+def _feats_layout(feats):
+    """(V,B,C,H,W)-shaped tensor -> (storage tensor, layout flag): channels-last storage (a permuted view of a
+    (V,B,H,W,C) buffer) is used in place, anything else is handed over as contiguous NCHW and re-laid out by the library."""
+    if feats.dim() != 5:
+        raise ValueError("feats must be (n_views, batch, C, H, W)")
+    nhwc_view = feats.permute(0, 1, 3, 4, 2)
+    if nhwc_view.is_contiguous():
+        return nhwc_view, _lib.FEATS_NHWC
+    return feats.contiguous(), _lib.FEATS_NCHW
+
+
+def back_project_forward(coords, origin, voxel_size, feats, KRcam, cell_hist=False, nchw=False):
+    """Kernel-level forward.  `feats`: channels-last maps (V,B,H,W,C), or with nchw=True the reference layout (V,B,C,H,W)
+    (re-laid out by the same launch that clears the binning state).  Returns (volume (N,C+1), count (N,)) and, with
+    cell_hist=True, additionally the int32 binning state the backward pass starts from."""
     L = _lib.lib()
-    dev = feats_nhwc.device
-    V, B, H, W, C = feats_nhwc.shape
+    dev = feats.device
+    if nchw:
+        V, B, C, H, W = feats.shape
+    else:
+        V, B, H, W, C = feats.shape
     N = coords.shape[0]
     if origin.shape != (B, 3) or KRcam.shape != (V, B, 4, 4):
         raise ValueError("origin must be (B,3) and KRcam (V,B,4,4) for feats (V,B,C,H,W)")
@@ -155,12 +170,13 @@ def back_project_forward(coords, origin, voxel_size, feats_nhwc, KRcam, cell_his
     if cell_hist:
         hist = _new_cell_hist(N, B, V, H, W, dev)
     if N > 0:
+        scratch = torch.empty((V, B, H, W, C), dtype=torch.float32, device=dev) if nchw else None
         ws, ws_bytes = _workspace("f", (N, B, V, C), dev)
         with _on_device(dev):
             rc = L.d3m_back_project_fwd(coords.data_ptr(), _COORD_KIND[coords.dtype], N, origin.data_ptr(), B,
-                                        float(voxel_size), feats_nhwc.data_ptr(), V, C, H, W, KRcam.data_ptr(),
-                                        out.data_ptr(), count.data_ptr(), _ptr(hist), ws.data_ptr(), ws_bytes,
-                                        _stream(dev))
+                                        float(voxel_size), feats.data_ptr(), _lib.FEATS_NCHW if nchw else _lib.FEATS_NHWC,
+                                        _ptr(scratch), V, C, H, W, KRcam.data_ptr(), out.data_ptr(), count.data_ptr(),
+                                        _ptr(hist), ws.data_ptr(), ws_bytes, _stream(dev))
         _lib.check(rc, "d3m_back_project_fwd")
     return (out, count, hist) if cell_hist else (out, count)
 
@@ -203,16 +219,18 @@ class _BackProject(torch.autograd.Function):
             feats = feats.float()
         dev = feats.device
         coords, origin, KRcam = _prep_small(coords, origin, KRcam, dev)
-        nhwc = feats_to_channels_last(feats)
+        store, layout = _feats_layout(feats)
+        nchw = layout == _lib.FEATS_NCHW
         if ctx.needs_input_grad[0]:
             # backward will follow: let the forward pass, which projects every voxel anyway, histogram the samples
-            out, count, hist = back_project_forward(coords, origin, voxel_size, nhwc, KRcam, cell_hist=True)
+            out, count, hist = back_project_forward(coords, origin, voxel_size, store, KRcam, cell_hist=True, nchw=nchw)
             ctx.save_for_backward(coords, origin, KRcam, count, hist)
         else:
-            out, count = back_project_forward(coords, origin, voxel_size, nhwc, KRcam)
+            out, count = back_project_forward(coords, origin, voxel_size, store, KRcam, nchw=nchw)
             ctx.save_for_backward(coords, origin, KRcam, count)
+        V, B, C, H, W = feats.shape
         ctx.voxel_size = float(voxel_size)
-        ctx.nhwc_shape = tuple(nhwc.shape)
+        ctx.nhwc_shape = (V, B, H, W, C)
         ctx.mark_non_differentiable(count)
         ctx.set_materialize_grads(False)
         return out, count

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 105
+#define D3M_VERSION 106
 
 enum {
   D3M_OK = 0,
@@ -77,23 +77,30 @@ int d3m_feats_nhwc_to_nchw(const float* src, float* dst, int64_t n_maps, int C, 
  * back_project forward  (replaces back_project.py:23-84)
  *   coords      (N,4) rows [batch, x, y, z] in voxel units, dtype per coords_kind
  *   origin      (B,3) float32 metres            voxel_size  float (python float in the reference)
- *   feats_nhwc  (V,B,H,W,C) float32             KRcam       (V,B,4,4) float32 world->pixel
+ *   KRcam       (V,B,4,4) float32 world->pixel
  *   out         (N,C+1) float32: view-mean features | normalised mean depth   (written for every row;
  *               rows whose batch index is outside [0,B) are zero, as in the reference)
  *   count       (N,) float32: number of views that see the voxel (bit-exact contract)
- *   cell_hist   NULL, or d3m_back_project_cell_hist_elems(N,B,V,H,W) int32 (16-byte aligned): receives the number of
- *               valid samples per bin = (bilinear cell (v,b,y0,x0), voxel-index bucket).  It is the first step of the
- *               deterministic backward; producing it here, where every voxel is projected anyway, saves the backward
- *               one full projection pass.  Pass it to d3m_back_project_bwd for the SAME coords / KRcam (the autograd
- *               wrapper does when feats needs grad).
+ *   feats       the per-view maps, float32, in either layout (feats_layout):
+ *                 D3M_FEATS_NCHW  (V,B,C,H,W) as torch.stack hands them over (models/neucon_network.py:128); then
+ *                                 feats_nhwc_scratch (V*B*H*W*C floats, 16-byte aligned) receives the channels-last copy
+ *                                 the gather reads (written by the same launch that clears the binning state);
+ *                 D3M_FEATS_NHWC  (V,B,H,W,C), used in place; feats_nhwc_scratch may be NULL.
+ *   cell_hist   NULL, or d3m_back_project_cell_hist_elems(N,B,V,H,W) int32 (16-byte aligned), contents arbitrary on entry:
+ *               the BINNING STATE the deterministic backward starts from -- samples per bin = (bilinear cell (v,b,y0,x0),
+ *               voxel-index bucket), histogrammed by the gather (which projects every voxel anyway) and already scanned
+ *               on return.  Pass it to d3m_back_project_bwd for the SAME coords / KRcam (the autograd wrapper does when
+ *               feats needs grad); backward may then run any number of times on it.
  * workspace: d3m_back_project_fwd_workspace(N,B,V,C) bytes, 256-byte aligned.
+ * Launches per call: relayout+clear, gather (+ depth statistics when B == 1), scan+normalise -- three.
  * ------------------------------------------------------------------------------------------- */
+enum { D3M_FEATS_NHWC = 0, D3M_FEATS_NCHW = 1 };
 size_t d3m_back_project_fwd_workspace(int64_t N, int B, int V, int C);
 size_t d3m_back_project_cell_hist_elems(int64_t N, int B, int V, int H, int W);
 int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
-                         float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                         const float* KRcam, float* out, float* count, int* cell_hist, void* workspace,
-                         size_t workspace_bytes, void* stream);
+                         float voxel_size, const float* feats, int feats_layout, float* feats_nhwc_scratch,
+                         int V, int C, int H, int W, const float* KRcam, float* out, float* count, int* cell_hist,
+                         void* workspace, size_t workspace_bytes, void* stream);
 
 /* Voxel-range sharding (BASELINE config 5): every rank runs the gather on its contiguous slice of the coordinate
  * list; the only cross-voxel coupling of the reference, the per-fragment depth normalisation
@@ -104,9 +111,10 @@ int d3m_back_project_fwd(const void* coords, int coords_kind, int64_t N, const f
  *   _finish   takes the (all-reduced) sums, derives mean / L2-norm and normalises out[:,C] in place.  `workspace`
  *             must be the buffer handed to _partial for the same slice, untouched in between. */
 int d3m_back_project_fwd_partial(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
-                                 float voxel_size, const float* feats_nhwc, int V, int C, int H, int W,
-                                 const float* KRcam, float* out, float* count, int* cell_hist, double* depth_sums,
-                                 void* workspace, size_t workspace_bytes, void* stream);
+                                 float voxel_size, const float* feats, int feats_layout, float* feats_nhwc_scratch,
+                                 int V, int C, int H, int W, const float* KRcam, float* out, float* count,
+                                 int* cell_hist, double* depth_sums, void* workspace, size_t workspace_bytes,
+                                 void* stream);
 int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sums, float* out, void* workspace,
                                 size_t workspace_bytes, void* stream);
 
@@ -119,15 +127,17 @@ int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sum
  *   grad_out         (N,C+1) float32 (the depth column carries no gradient to feats)
  *   count            (N,) float32 as returned by d3m_back_project_fwd for the same inputs, or NULL
  *                    (then the view counts are recomputed by one extra kernel)
- *   cell_hist        histogram produced by d3m_back_project_fwd for the same inputs (read-only here, so
- *                    backward may run more than once), or NULL (then one extra projection pass rebuilds it)
+ *   cell_hist        binning state produced by d3m_back_project_fwd for the same inputs (its claim counters are used
+ *                    and handed back cleared, so backward may run more than once), or NULL (then the state is rebuilt
+ *                    in the workspace: clear + projection/histogram pass + scan, three extra launches)
+ * Launches per call with count and cell_hist: fill+pre-division, gather -- two.
  *   grad_feats       float32, fully overwritten; (V,B,H,W,C) when grad_nchw == 0, the reference's
  *                    (V,B,C,H,W) when grad_nchw != 0 (the gather kernel then stores channel-strided)
  * ------------------------------------------------------------------------------------------- */
 size_t d3m_back_project_bwd_workspace(int64_t N, int B, int V, int C, int H, int W);
 int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
                          float voxel_size, int V, int C, int H, int W, const float* KRcam,
-                         const float* grad_out, const float* count, const int* cell_hist, float* grad_feats,
+                         const float* grad_out, const float* count, int* cell_hist, float* grad_feats,
                          int grad_nchw, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------

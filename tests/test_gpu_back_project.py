@@ -185,10 +185,19 @@ def test_backward_without_forward_count_recomputes_it():
     # the forward pass can also hand over the per-cell sample histogram (what the autograd wrapper does)
     vol2, cnt2, hist = voxel.back_project_forward(coords, origin, 0.04, nhwc, KR, cell_hist=True)
     assert torch.equal(vol, vol2) and torch.equal(cnt, cnt2)
-    assert int(hist.sum()) == int(cnt.sum()) and hist.dtype == torch.int32
+    # binning state (include/d3m.h, BinLayout): [histogram Mb | claim counters Mb | look-back words | counters | scan Mb+1]
+    M = int(np.prod(shape[:4]))
+    scan0 = hist.numel() - (M + 1 + 3) // 4 * 4          # every section is padded to 16 bytes
+    assert hist.dtype == torch.int32 and int(hist[:M].sum()) == int(cnt.sum())
+    assert int(hist[M:scan0].abs().sum()) == 0, "claim counters / look-back words must come back cleared"
+    assert int(hist[scan0]) == 0 and int(hist[scan0 + M]) == int(cnt.sum()), "exclusive scan: 0 ... number of valid samples"
     g4 = voxel.back_project_backward(coords, origin, 0.04, shape, KR, go, count=cnt, cell_hist=hist)
-    g5 = voxel.back_project_backward(coords, origin, 0.04, shape, KR, go, count=cnt, cell_hist=hist)  # hist is read-only
+    assert int(hist[M:scan0].abs().sum()) == 0, "backward must hand the state back cleared"
+    g5 = voxel.back_project_backward(coords, origin, 0.04, shape, KR, go, count=cnt, cell_hist=hist)  # state is re-usable
     assert torch.equal(g1, g4) and torch.equal(g1, g5)
+    # the reference layout straight into the C call (relayout fused with the state clear) gives the same bits
+    vol3, cnt3, hist3 = voxel.back_project_forward(coords, origin, 0.04, t(inp["feats"]), KR, cell_hist=True, nchw=True)
+    assert torch.equal(vol, vol3) and torch.equal(cnt, cnt3) and torch.equal(hist[:scan0 + M + 1], hist3[:scan0 + M + 1])
 
 
 def test_backward_twice_with_retain_graph():
