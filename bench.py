@@ -878,38 +878,38 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     mine = shard.voxel_blocks(N, rank, world)
     coords = torch.from_numpy(np.ascontiguousarray(coords_all[mine.numpy()])).to(dev)
     n_local = int(mine.numel())
-    inv_perm = shard.blocks_inverse_permutation(N, world).to(dev) if world > 1 else None
     R, c = synth.large_scene_cameras(V)
     KR = torch.from_numpy(synth.krcam_from(R, c, synth.scaled_K(L["scale"]))[:, None].copy()).to(dev)
     origin = torch.zeros((1, 3), device=dev)
     gen = torch.Generator(device=dev)
     gen.manual_seed(777)  # same seed on every rank: replicated feature maps
-    feats = torch.randn((V, 1, L["C"], L["H"], L["W"]), device=dev, generator=gen).requires_grad_(True)
+    feats = torch.randn((V, 1, L["C"], L["H"], L["W"]), device=dev, generator=gen)
     gen.manual_seed(778)  # same seed on every rank: grad_out of the whole scene, each rank keeps the rows of its voxels
     go_all = torch.randn((N, L["C"] + 1), device=dev, generator=gen)
     go = go_all[mine.to(dev)].contiguous() if world > 1 else go_all
-    sizes = [int(shard.voxel_blocks(N, r, world).numel()) for r in range(world)]
-
     def step():
-        feats.grad = None
-        vol, cnt = shard.back_project_voxel_sharded(coords, origin, synth.VOXEL_SIZE, feats, KR)
-        vol.backward(go)
-        full = shard.all_gather_rows(cnt, sizes=sizes)
-        return (full[inv_perm] if inv_perm is not None else full), cnt  # occupancy in the scene's voxel order
+        # forward (all-reduce of 3 fp64 depth sums) + backward with the fused view-owner exchange: every rank ends with the
+        # gradient of ITS V / world views (what a view-parallel 2D backbone consumes) + all-gather of the view counts
+        # (peer stores of every rank's rows at their positions in the scene's voxel order: no gather collective)
+        vol, cnt, grad_fn, full = shard.back_project_voxel_sharded_view_owner(coords, origin, synth.VOXEL_SIZE, feats, KR,
+                                                                              count_rows=(N, 0, 4096))
+        g_own, vr = grad_fn(go)
+        return full, cnt, g_own, vr
 
     for _ in range(2):
-        full_cnt, cnt = step()
+        full_cnt, cnt, g_own, vr = step()
     torch.cuda.synchronize()
     # ---- parity of the multi-rank path, on the real shape, every run ----------------------------------------------
     parity = {"checked": False, "why": "single rank: sharded == unsharded by construction"}
     if world > 1:
         ok = torch.ones(1, device=dev)
+        g_full = shard.all_gather_rows(g_own)       # owned view ranges in rank order == views 0..V-1 (outside the timed region)
         if rank == 0:
             f_ref = feats.detach().clone().requires_grad_(True)
             v_ref, c_ref = back_project(torch.from_numpy(coords_all).to(dev), origin, synth.VOXEL_SIZE, f_ref, KR)
             v_ref.backward(go_all)
-            count_equal = bool(torch.equal(full_cnt, c_ref))
-            err = (feats.grad.double() - f_ref.grad.double())
+            count_equal = bool(torch.equal(full_cnt, c_ref)) and tuple(g_full.shape) == tuple(f_ref.grad.shape)
+            err = (g_full.double() - f_ref.grad.double())
             ref_l2 = float(f_ref.grad.double().norm())
             ref_max = float(f_ref.grad.abs().max())
             rel_l2 = float(err.norm()) / max(ref_l2, 1e-30)
@@ -920,6 +920,7 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
                       "against": "unsharded back_project of all %d voxels on rank 0 (same feats / grad_out)" % N}
             ok[0] = 1.0 if parity["pass"] else 0.0
             del f_ref, v_ref, c_ref, err
+        del g_full
         dist.broadcast(ok, 0)
         if float(ok[0]) != 1.0:
             raise AssertionError("large-scene multi-rank parity FAILED: %r" % (parity,))
@@ -949,8 +950,10 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     res = {"kernel_ms_rank0": kern, "index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": n_local, "partition": "block-cyclic voxel ranges (4096 voxels per block)",
            "samples_per_step": int(N) * V, "valid_samples": int(S[0].item()), "ms_per_step": ms,
            "samples_per_s": N * V / (ms * 1e-3), "scaling": "strong", "parity": parity,
-           "collectives": "all_reduce(3 fp64 per fragment) + %s(grad_feats %.0f MB) + all_gather(count, %d B/voxel)"
-                          % (shard.grad_exchange_name(), feats.numel() * 4 / 1e6, 4), "full_count_rows": int(full_cnt.shape[0])}
+           "collectives": "all_reduce(3 fp64 per fragment) + grad_feats %.0f MB by %s + view counts (%d B/voxel) all-gathered as "
+                          "peer stores + one 4-byte all-reduce as the barrier of the backward exchange"
+                          % (feats.numel() * 4 / 1e6, shard.grad_exchange_name(), 4),
+           "grad_views_owned_rank0": list(vr), "full_count_rows": int(full_cnt.shape[0])}
     del coords, feats, go
     torch.cuda.empty_cache()
     return res

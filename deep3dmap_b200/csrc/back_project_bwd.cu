@@ -29,6 +29,7 @@ namespace d3m {
 
 constexpr unsigned kFullB = 0xffffffffu;
 constexpr int kGatherWarps = 8;
+constexpr int kMaxExchangeRanks = 16;
 
 struct BwdParams {
   const void* coords;
@@ -51,6 +52,11 @@ struct BwdParams {
   int64_t Mb;     // M << nb_log2 bins (cell-major, voxel-bucket-minor; see BinCfg)
   int nb_log2;
   int grad_nchw;                   // 1: gather writes (V,B,C,H,W) directly
+  // view-owner exchange (voxel-range sharding over several GPUs): the gather stores every texel straight into the staging
+  // buffer of the rank that owns the texel's view -- peer memory over NVLink -- in slot `xchg_rank` of that buffer
+  int xchg_world;                  // 0 = off
+  int xchg_rank, xchg_vpo;         // this rank; views per owner
+  float* xchg_peer[kMaxExchangeRanks];  // staging buffer of every rank, (world, vpo, B, H, W, C), mapped in this process
   // fill + ghat launch
   int fill_ctas_x, fill_ctas;      // voxel CTAs per view group; fill CTAs in total (the CTAs behind them write ghat)
 };
@@ -406,7 +412,14 @@ __global__ void __launch_bounds__(kGatherWarps * 32, (R == 1 ? 4 : 3)) bp_bwd_ga
       a.y = __fadd_rn(__fadd_rn(__fadd_rn(a.y, b1.y), b2.y), b3.y);
       a.z = __fadd_rn(__fadd_rn(__fadd_rn(a.z, b1.z), b2.z), b3.z);
       a.w = __fadd_rn(__fadd_rn(__fadd_rn(a.w, b1.w), b2.w), b3.w);
-      if (!p.grad_nchw) {
+      if (p.xchg_world) {
+        // owner's staging slot of this rank, channels-last: one 16-byte store per lane, C contiguous floats per texel
+        const int v = map / p.B, b = map - v * p.B;
+        const int owner = v / p.xchg_vpo, vl = v - owner * p.xchg_vpo;
+        float4* dst = reinterpret_cast<float4*>(p.xchg_peer[owner]) +
+                      ((((int64_t)p.xchg_rank * p.xchg_vpo + vl) * p.B + b) * hw + (int64_t)y * p.W + x) * C4;
+        dst[o] = a;
+      } else if (!p.grad_nchw) {
         reinterpret_cast<float4*>(p.grad_feats)[tex * C4 + o] = a;
       } else {
         // (V,B,C,H,W): channel c of texel (map, y, x) lives at ((map*C + c)*H + y)*W + x
@@ -648,11 +661,15 @@ extern "C" size_t d3m_back_project_bwd_workspace(int64_t N, int B, int V, int C,
   return bwd_ws_layout(N, B, V, C, H, W).total;
 }
 
-extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
-                                    float voxel_size, int V, int C, int H, int W, const float* KRcam,
-                                    const float* grad_out, const float* count, int* cell_hist,
-                                    float* grad_feats_nhwc, int grad_nchw, void* workspace, size_t workspace_bytes,
-                                    void* stream_) {
+struct Exchange {
+  void* const* peer_bufs;   // host array of `world` device pointers (every rank's staging buffer, mapped here)
+  int world, rank;
+};
+
+static int bwd_impl(const void* coords, int coords_kind, int64_t N, const float* origin, int B, float voxel_size, int V,
+                    int C, int H, int W, const float* KRcam, const float* grad_out, const float* count, int* cell_hist,
+                    float* grad_feats_nhwc, int grad_nchw, void* workspace, size_t workspace_bytes, const Exchange* xc,
+                    void* stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE,
               "back_project backward: no CUDA device (there is no CPU fallback)");
@@ -662,10 +679,28 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
   D3M_REQUIRE((int64_t)V * B * H * W < (1ll << 30), D3M_ERR_ARG, "back_project backward: V*B*H*W must be < 2^30");
   D3M_REQUIRE(V <= 65535, D3M_ERR_ARG, "back_project backward: too many views");
   D3M_REQUIRE(N * (int64_t)V < (1ll << 31), D3M_ERR_ARG, "back_project backward: N*V must be < 2^31 samples");
-  D3M_REQUIRE(grad_feats_nhwc && workspace, D3M_ERR_ARG, "back_project backward: NULL pointer");
+  D3M_REQUIRE((grad_feats_nhwc || xc) && workspace, D3M_ERR_ARG, "back_project backward: NULL pointer");
   const BwdWs w = bwd_ws_layout(N, B, V, C, H, W);
+  int vpo = 0;
+  if (xc) {
+    D3M_REQUIRE(xc->peer_bufs && xc->world >= 1 && xc->world <= kMaxExchangeRanks && xc->rank >= 0 && xc->rank < xc->world,
+                D3M_ERR_ARG, "back_project backward exchange: bad world / rank (at most %d ranks)", kMaxExchangeRanks);
+    D3M_REQUIRE((C & 3) == 0 && pick_gather_kernel(C) != nullptr, D3M_ERR_ARG,
+                "back_project backward exchange: C=%d has no tiled gather kernel", C);
+    vpo = (V + xc->world - 1) / xc->world;
+    for (int r = 0; r < xc->world; ++r)
+      D3M_REQUIRE(xc->peer_bufs[r] && aligned16(xc->peer_bufs[r]), D3M_ERR_ALIGN,
+                  "back_project backward exchange: staging buffer of rank %d is NULL or unaligned", r);
+  }
   if (N == 0) {
-    D3M_CUDA_CHECK(cudaMemsetAsync(grad_feats_nhwc, 0, sizeof(float) * (size_t)w.bl.M * C, stream));
+    if (!xc) {
+      D3M_CUDA_CHECK(cudaMemsetAsync(grad_feats_nhwc, 0, sizeof(float) * (size_t)w.bl.M * C, stream));
+      return D3M_OK;
+    }
+    // an empty shard still owes every owner a slot of zeros
+    const size_t slot = sizeof(float) * (size_t)vpo * B * H * W * C;
+    for (int r = 0; r < xc->world; ++r)
+      D3M_CUDA_CHECK(cudaMemsetAsync(static_cast<unsigned char*>(xc->peer_bufs[r]) + slot * xc->rank, 0, slot, stream));
     return D3M_OK;
   }
   D3M_REQUIRE(coords && origin && KRcam && grad_out, D3M_ERR_ARG, "back_project backward: NULL pointer");
@@ -690,9 +725,78 @@ extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t
   p.grad_feats = grad_feats_nhwc;
   p.M = w.bl.M; p.Mb = w.bl.Mb; p.nb_log2 = w.bl.nb_log2;
   p.grad_nchw = grad_nchw ? 1 : 0;
+  if (xc) {
+    p.xchg_world = xc->world; p.xchg_rank = xc->rank; p.xchg_vpo = vpo;
+    for (int r = 0; r < xc->world; ++r) p.xchg_peer[r] = static_cast<float*>(xc->peer_bufs[r]);
+  }
   float* cnt_ws = count ? nullptr : reinterpret_cast<float*>(ws + w.cnt);
   p.count = count ? count : cnt_ws;
   if (coords_kind == D3M_COORDS_F32) return launch_bwd<D3M_COORDS_F32>(p, bins, w.bl, own_state, cnt_ws, stream);
   if (coords_kind == D3M_COORDS_I64) return launch_bwd<D3M_COORDS_I64>(p, bins, w.bl, own_state, cnt_ws, stream);
   return launch_bwd<D3M_COORDS_I32>(p, bins, w.bl, own_state, cnt_ws, stream);
 }
+
+extern "C" int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                    float voxel_size, int V, int C, int H, int W, const float* KRcam,
+                                    const float* grad_out, const float* count, int* cell_hist,
+                                    float* grad_feats_nhwc, int grad_nchw, void* workspace, size_t workspace_bytes,
+                                    void* stream_) {
+  return bwd_impl(coords, coords_kind, N, origin, B, voxel_size, V, C, H, W, KRcam, grad_out, count, cell_hist,
+                  grad_feats_nhwc, grad_nchw, workspace, workspace_bytes, nullptr, stream_);
+}
+
+extern "C" int d3m_back_project_bwd_exchange(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                             float voxel_size, int V, int C, int H, int W, const float* KRcam,
+                                             const float* grad_out, const float* count, int* cell_hist,
+                                             void* const* peer_staging_host, int world, int rank, void* workspace,
+                                             size_t workspace_bytes, void* stream_) {
+  Exchange xc;
+  xc.peer_bufs = peer_staging_host; xc.world = world; xc.rank = rank;
+  return bwd_impl(coords, coords_kind, N, origin, B, voxel_size, V, C, H, W, KRcam, grad_out, count, cell_hist, nullptr, 0,
+                  workspace, workspace_bytes, &xc, stream_);
+}
+
+// ---- owner side of the exchange: sum the `world` slots of this rank's staging buffer in rank order ----------------------
+// staging (world, vpo, B, H, W, C) channels-last -> out (n_views, B, C, H, W) in the reference layout; n_views <= vpo is the
+// number of views this rank really owns.  One thread per (texel, channel quad); the slots are added in ascending rank
+// order, so the result does not depend on arrival order.
+namespace d3m {
+__global__ void __launch_bounds__(256) grad_slots_sum_kernel(const float4* __restrict__ staging, float* __restrict__ out,
+                                                             int world, int vpo, int n_views, int B, int C4, int64_t hw) {
+  pdl_enter();
+  const int64_t total = (int64_t)n_views * B * hw * C4;
+  const int64_t slot = (int64_t)vpo * B * hw * C4;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    float4 a = __ldcs(staging + i);
+    for (int r = 1; r < world; ++r) {
+      const float4 t = __ldcs(staging + r * slot + i);
+      a.x = __fadd_rn(a.x, t.x); a.y = __fadd_rn(a.y, t.y); a.z = __fadd_rn(a.z, t.z); a.w = __fadd_rn(a.w, t.w);
+    }
+    const int q = (int)(i % C4);
+    const int64_t tex = i / C4;              // (view, b, y, x) linear
+    const int64_t yx = tex % hw, vb = tex / hw;
+    float* dst = out + (vb * C4 * 4 + (int64_t)q * 4) * hw + yx;
+    dst[0] = a.x; dst[hw] = a.y; dst[2 * hw] = a.z; dst[3 * hw] = a.w;
+  }
+}
+}  // namespace d3m
+
+extern "C" int d3m_grad_slots_sum(const float* staging, int world, int views_per_owner, int n_views, int B, int C, int H,
+                                  int W, float* out_nchw, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "grad_slots_sum: no CUDA device");
+  D3M_REQUIRE(world >= 1 && views_per_owner >= 1 && n_views >= 0 && n_views <= views_per_owner && B >= 1 && C >= 4 &&
+                  (C & 3) == 0 && H >= 1 && W >= 1,
+              D3M_ERR_ARG, "grad_slots_sum: bad arguments");
+  if (n_views == 0) return D3M_OK;
+  D3M_REQUIRE(staging && out_nchw && aligned16(staging), D3M_ERR_ARG, "grad_slots_sum: NULL / unaligned pointer");
+  const int64_t total = (int64_t)n_views * B * H * W * (C / 4);
+  int64_t ctas = (total + 255) / 256;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  LaunchScope ls("grad_slots_sum", stream);
+  launch_k(grad_slots_sum_kernel, dim3((unsigned)ctas), dim3(256), 0, stream, reinterpret_cast<const float4*>(staging),
+           out_nchw, world, views_per_owner, n_views, B, C / 4, (int64_t)H * W);
+  D3M_CUDA_CHECK(cudaGetLastError());
+  return D3M_OK;
+}
+

@@ -195,3 +195,84 @@ extern "C" int d3m_feats_nchw_to_nhwc(const float* src, float* dst, int64_t n_ma
 extern "C" int d3m_feats_nhwc_to_nchw(const float* src, float* dst, int64_t n_maps, int C, int H, int W, void* stream) {
   return d3m::transpose_maps(src, dst, n_maps, H * W, C, static_cast<cudaStream_t>(stream));
 }
+
+// ---- peer-visible device memory (one process per GPU, one box): CUDA IPC -------------------------------------------
+// The exchange buffers of the voxel-sharded backward live in plain cudaMalloc memory owned by this library; the 64-byte
+// IPC handle travels through the caller's process group (torch.distributed.all_gather_object) and every peer maps the
+// buffer into its own address space.  Kernels then store to it directly over NVLink.
+extern "C" int d3m_p2p_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64_host) {
+  D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "d3m_p2p_alloc: no CUDA device");
+  D3M_REQUIRE(bytes > 0 && dev_ptr && handle64_host, D3M_ERR_ARG, "d3m_p2p_alloc: bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  void* p = nullptr;
+  D3M_CUDA_CHECK(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) { cudaFree(p); return d3m::cuda_fail(e, "cudaIpcGetMemHandle"); }
+  memcpy(handle64_host, &h, 64);
+  *dev_ptr = p;
+  return D3M_OK;
+}
+
+extern "C" int d3m_p2p_open(const unsigned char* handle64_host, void** dev_ptr) {
+  D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "d3m_p2p_open: no CUDA device");
+  D3M_REQUIRE(handle64_host && dev_ptr, D3M_ERR_ARG, "d3m_p2p_open: bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64_host, 64);
+  D3M_CUDA_CHECK(cudaIpcOpenMemHandle(dev_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return D3M_OK;
+}
+
+extern "C" int d3m_p2p_close(void* dev_ptr) {
+  if (!dev_ptr) return D3M_OK;
+  D3M_CUDA_CHECK(cudaIpcCloseMemHandle(dev_ptr));
+  return D3M_OK;
+}
+
+extern "C" int d3m_p2p_free(void* dev_ptr) {
+  if (!dev_ptr) return D3M_OK;
+  D3M_CUDA_CHECK(cudaFree(dev_ptr));
+  return D3M_OK;
+}
+
+// ---- all-gather of per-voxel rows as peer stores --------------------------------------------------------------------
+// Every rank writes its n_local rows (row_words 32-bit words each) into EVERY rank's full-size buffer at the rows' global
+// positions: contiguous ranges (block == 0: global = begin + i) or block-cyclic ranges (global = ((i / block) * world +
+// rank) * block + i % block, shard.voxel_blocks).  The next collective of the caller on the same streams (the all-reduce
+// of the depth sums) is the barrier after which every buffer is complete: no gather collective, no padding, no
+// re-ordering pass (the rows land in the scene's voxel order).
+namespace d3m {
+__global__ void __launch_bounds__(256) p2p_scatter_rows_kernel(const uint32_t* __restrict__ src, int64_t n_local, int row_words,
+                                                               int64_t begin, int64_t block, int world, int rank,
+                                                               uint32_t* const* __restrict__ peers) {
+  pdl_enter();
+  const int64_t total = n_local * row_words;
+  for (int64_t k = (int64_t)blockIdx.x * 256 + threadIdx.x; k < total; k += (int64_t)gridDim.x * 256) {
+    const int64_t i = k / row_words;
+    const int w = (int)(k - i * row_words);
+    const int64_t g = block > 0 ? ((i / block) * world + rank) * block + i % block : begin + i;
+    const uint32_t v = __ldg(src + k);
+    for (int r = 0; r < world; ++r) peers[r][g * row_words + w] = v;
+  }
+}
+}  // namespace d3m
+
+extern "C" int d3m_p2p_scatter_rows(const void* src, int64_t n_local, int row_bytes, int64_t begin, int64_t block,
+                                    void* const* peer_dst_dev_table, int world, int rank, void* stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  D3M_REQUIRE(d3m_device_count() > 0, D3M_ERR_NO_DEVICE, "d3m_p2p_scatter_rows: no CUDA device");
+  D3M_REQUIRE(n_local >= 0 && row_bytes >= 4 && row_bytes % 4 == 0 && begin >= 0 && block >= 0 && world >= 1 && rank >= 0 &&
+                  rank < world && peer_dst_dev_table,
+              D3M_ERR_ARG, "d3m_p2p_scatter_rows: bad arguments");
+  if (n_local == 0) return D3M_OK;
+  D3M_REQUIRE(src, D3M_ERR_ARG, "d3m_p2p_scatter_rows: NULL source");
+  const int64_t total = n_local * (row_bytes / 4);
+  int64_t ctas = (total + 255) / 256;
+  if (ctas > 148 * 8) ctas = 148 * 8;
+  d3m::LaunchScope ls("p2p_scatter_rows", stream);
+  d3m::launch_k(d3m::p2p_scatter_rows_kernel, dim3((unsigned)ctas), dim3(256), 0, stream, static_cast<const uint32_t*>(src),
+                n_local, row_bytes / 4, begin, block, world, rank, reinterpret_cast<uint32_t* const*>(peer_dst_dev_table));
+  D3M_CUDA_CHECK(cudaGetLastError());
+  return D3M_OK;
+}
+

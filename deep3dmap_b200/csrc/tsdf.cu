@@ -542,7 +542,7 @@ __global__ void __launch_bounds__(kTsdfThreads, 4) tsdf_integrate_kernel(const T
       }
       if (pend_upd == 0u) return;
       const float obs = pend_obs;
-      if (SL) {   // all four quotients, then select
+      if constexpr (SL) {   // all four quotients, then select
 #pragma unroll
         for (int i = 0; i < kVoxPerThread; ++i) {
           const float w_new = __fadd_rn(wv[i], obs);
@@ -554,7 +554,7 @@ __global__ void __launch_bounds__(kTsdfThreads, 4) tsdf_integrate_kernel(const T
         dirty |= pend_upd;
         pend_upd = 0u;
         return;
-      }
+      } else {
 #pragma unroll
       for (int i = 0; i < kVoxPerThread; ++i) {
         if (!((pend_upd >> i) & 1u)) continue;
@@ -586,6 +586,7 @@ __global__ void __launch_bounds__(kTsdfThreads, 4) tsdf_integrate_kernel(const T
       }
       dirty |= pend_upd;
       pend_upd = 0u;
+      }
     };
     // ---- frames in order, one mask word (32 frames) at a time: lane j decides for frame 32w + j whether it can touch
     // THIS sub-box; the warp then walks the surviving frames of the word in order

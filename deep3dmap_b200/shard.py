@@ -180,8 +180,208 @@ class _CudaLocalOps:
 
 
 def grad_exchange_name():
-    """Which collective `back_project_voxel_sharded`'s backward uses for grad_feats (reported by bench.py)."""
-    return "all_reduce"
+    """Which exchange bench.py's large-scene leg times for grad_feats."""
+    return "fused view-owner exchange (peer stores from the gather kernel + rank-ordered slot sum)"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# fused view-owner exchange of grad_feats (reduce-scatter by view, without a collective on the data)
+# ---------------------------------------------------------------------------------------------------------------
+class GradExchange:
+    """Staging buffers of the fused backward exchange for one feature-map shape (V, B, C, H, W).
+
+    Every rank owns `vpo = ceil(V / world)` consecutive views and a staging buffer of `world` slots (one per sending
+    rank) for them, channels-last, in cudaMalloc memory of libd3m whose CUDA-IPC handle is exchanged ONCE through the
+    process group; the peers' buffers are mapped into this process.  The gather kernel of every rank then stores its
+    partial gradient of view v directly into slot `rank` of owner(v)'s buffer over NVLink.  Two buffers alternate between
+    calls: a rank can only be one call ahead of the slowest one (the barrier inside every call), so it never overwrites a
+    slot its owner is still summing."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, shape, device, group=None):
+        key = (tuple(int(x) for x in shape), device.index, id(group))
+        ex = cls._cache.get(key)
+        if ex is None:
+            ex = cls._cache[key] = cls(shape, device, group)
+        return ex
+
+    def __init__(self, shape, device, group=None):
+        import ctypes
+        self.V, self.B, self.C, self.H, self.W = (int(x) for x in shape)
+        self.rank, self.world = _world(group)
+        self.group, self.device = group, device
+        self.vpo = (self.V + self.world - 1) // self.world
+        self.v0 = min(self.V, self.rank * self.vpo)
+        self.v1 = min(self.V, self.v0 + self.vpo)
+        self.slot_floats = self.vpo * self.B * self.H * self.W * self.C
+        nbytes = 4 * self.world * self.slot_floats
+        L = _lib.lib()
+        self._own, self._peers, self.tables = [], [], []
+        for _ in range(2):
+            ptr = ctypes.c_void_p()
+            handle = (ctypes.c_ubyte * 64)()
+            with voxel._on_device(device):
+                _lib.check(L.d3m_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "d3m_p2p_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(ptr.value)
+                    continue
+                q = ctypes.c_void_p()
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                with voxel._on_device(device):
+                    _lib.check(L.d3m_p2p_open(h, ctypes.byref(q)), "d3m_p2p_open (rank %d)" % r)
+                ptrs.append(q.value)
+                self._peers.append(q.value)
+            self._own.append(ptr.value)
+            self.tables.append((ctypes.c_void_p * self.world)(*ptrs))
+        self._turn = 0
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+
+    def next_table(self):
+        k = self._turn
+        self._turn ^= 1
+        return k, self.tables[k]
+
+    def barrier(self):
+        """All ranks' gather kernels issued before this call have completed (their peer stores have landed) once the
+        current stream passes this point: a 4-byte all-reduce ordered on the stream."""
+        dist.all_reduce(self._flag, group=self.group)
+
+    def sum_slots(self, k):
+        """-> (v1 - v0, B, C, H, W) gradient of this rank's views: its `world` slots added in ascending rank order."""
+        n_own = self.v1 - self.v0
+        out = torch.empty((n_own, self.B, self.C, self.H, self.W), dtype=torch.float32, device=self.device)
+        if n_own:
+            with voxel._on_device(self.device):
+                rc = _lib.lib().d3m_grad_slots_sum(self._own[k], self.world, self.vpo, n_own, self.B, self.C, self.H,
+                                                   self.W, out.data_ptr(), voxel._stream(self.device))
+            _lib.check(rc, "d3m_grad_slots_sum")
+        return out
+
+
+class _DevView:
+    """__cuda_array_interface__ over library-owned device memory (torch.as_tensor wraps it without a copy)."""
+
+    def __init__(self, ptr, shape, typestr, owner):
+        self.__cuda_array_interface__ = {"shape": tuple(int(x) for x in shape), "typestr": typestr, "data": (int(ptr), False),
+                                         "version": 2}
+        self._owner = owner
+
+
+class RowsExchange:
+    """All-gather of per-voxel float32 rows (view counts, occupancy) as peer stores instead of a collective: every rank
+    owns a full-size (n_total, width) buffer in IPC-shared memory and writes its rows straight into every rank's buffer at
+    their global positions (`d3m_p2p_scatter_rows`); the caller's next collective on the stream is the barrier.  Two
+    buffers alternate between calls (same argument as `GradExchange`)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, n_total, width, device, group=None):
+        key = (int(n_total), int(width), device.index, id(group))
+        ex = cls._cache.get(key)
+        if ex is None:
+            ex = cls._cache[key] = cls(n_total, width, device, group)
+        return ex
+
+    def __init__(self, n_total, width, device, group=None):
+        import ctypes
+        self.n_total, self.width, self.device, self.group = int(n_total), int(width), device, group
+        self.rank, self.world = _world(group)
+        L = _lib.lib()
+        nbytes = max(16, 4 * self.n_total * self.width)
+        self._own, self._tables, self._views = [], [], []
+        for _ in range(2):
+            ptr = ctypes.c_void_p()
+            handle = (ctypes.c_ubyte * 64)()
+            with voxel._on_device(device):
+                _lib.check(L.d3m_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "d3m_p2p_alloc")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            ptrs = []
+            for r in range(self.world):
+                if r == self.rank:
+                    ptrs.append(ptr.value)
+                    continue
+                q = ctypes.c_void_p()
+                h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+                with voxel._on_device(device):
+                    _lib.check(L.d3m_p2p_open(h, ctypes.byref(q)), "d3m_p2p_open (rank %d)" % r)
+                ptrs.append(q.value)
+            self._own.append(ptr.value)
+            self._tables.append(torch.tensor(ptrs, dtype=torch.int64, device=device))   # device-side pointer table
+            shape = (self.n_total, self.width) if self.width > 1 else (self.n_total,)
+            self._views.append(torch.as_tensor(_DevView(ptr.value, shape, "<f4", self), device=device))
+        self._turn = 0
+
+    def scatter(self, local, begin=0, block=0):
+        """Write this rank's rows into every rank's buffer; returns this rank's full buffer (complete after the next
+        collective on the current stream)."""
+        k = self._turn
+        self._turn ^= 1
+        local = local.contiguous()
+        with voxel._on_device(self.device):
+            rc = _lib.lib().d3m_p2p_scatter_rows(voxel._ptr(local), local.shape[0], 4 * self.width, int(begin), int(block),
+                                                 self._tables[k].data_ptr(), self.world, self.rank,
+                                                 voxel._stream(self.device))
+        _lib.check(rc, "d3m_p2p_scatter_rows")
+        return self._views[k]
+
+
+def back_project_voxel_sharded_view_owner(coords_local, origin, voxel_size, feats, KRcam, group=None, count_rows=None):
+    """Voxel-range sharded `back_project` whose backward ends with every rank holding the gradient of ITS views only --
+    the reduce-scatter-by-view a view-parallel 2D backbone consumes -- through the fused exchange of `GradExchange`.
+
+    Returns (volume_local, count_local, grad_fn); `grad_fn(grad_out_local) -> (grad (v1-v0, B, C, H, W), (v0, v1))`.
+    Forward is `back_project_voxel_sharded`'s (same bits); the gradient equals the corresponding views of the all-reduced
+    one up to the order in which the ranks' partial sums are added (ascending rank here).
+    `count_rows=(n_total, begin, block)`: additionally all-gather the view counts of the whole scene (what the next
+    coarse-to-fine level needs, neucon_network.py:132) as peer stores at the rows' global positions -- `begin` for a
+    contiguous `voxel_range`, `block` for `voxel_blocks` -- and return them as a 4th value, in the scene's voxel order."""
+    ops = _CudaLocalOps
+    out, count, sums, state = ops.forward_partial(coords_local, origin, voxel_size, feats.detach(), KRcam, want_hist=True)
+    rank, world = _world(group)
+    full_count = None
+    if count_rows is not None:
+        n_total, begin, block = count_rows
+        if world > 1:
+            full_count = RowsExchange.get(n_total, 1, out.device, group).scatter(count, begin=begin, block=block)
+        else:
+            full_count = count
+    if world > 1:
+        # 3 fp64 scalars per fragment -- and the barrier after which every rank's count rows have landed
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    out = ops.forward_finish(out, sums, state)
+    _, _, (V, B, H, W, C), coords, origin_d, KR, hist = state
+    dev = out.device
+
+    def grad_fn(grad_out):
+        g = grad_out if (grad_out.is_contiguous() and grad_out.dtype == torch.float32) else grad_out.contiguous().float()
+        if world == 1:
+            grad = voxel.back_project_backward(coords, origin_d, voxel_size, (V, B, H, W, C), KR, g, nchw=True, count=count,
+                                               cell_hist=hist)
+            return grad, (0, V)
+        ex = GradExchange.get((V, B, C, H, W), dev, group)
+        k, table = ex.next_table()
+        N = coords.shape[0]
+        ws, ws_bytes = voxel._workspace("b", (N, B, V, C, H, W), dev)
+        with voxel._on_device(dev):
+            rc = _lib.lib().d3m_back_project_bwd_exchange(
+                voxel._ptr(coords), voxel._COORD_KIND[coords.dtype], N, voxel._ptr(origin_d), B, float(voxel_size), V, C, H, W,
+                voxel._ptr(KR), voxel._ptr(g), voxel._ptr(count), voxel._ptr(hist), table, world, rank, ws.data_ptr(),
+                ws_bytes, voxel._stream(dev))
+        _lib.check(rc, "d3m_back_project_bwd_exchange")
+        ex.barrier()
+        return ex.sum_slots(k), (ex.v0, ex.v1)
+
+    if count_rows is not None:
+        return out, count, grad_fn, full_count
+    return out, count, grad_fn
 
 
 def grad_view_chunks(V, world):

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 106
+#define D3M_VERSION 108
 
 enum {
   D3M_OK = 0,
@@ -139,6 +139,40 @@ int d3m_back_project_bwd(const void* coords, int coords_kind, int64_t N, const f
                          float voxel_size, int V, int C, int H, int W, const float* KRcam,
                          const float* grad_out, const float* count, int* cell_hist, float* grad_feats,
                          int grad_nchw, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Voxel-range sharding over the GPUs of one box (BASELINE config 5): backward with a fused exchange.
+ * Every rank holds a slice of the voxel list and the (replicated) feature maps of ALL views, so its backward produces a
+ * partial gradient of every view.  Instead of materialising that partial gradient and all-reducing it (118 MB at 64 views),
+ * the gather kernel stores each texel tile straight into the staging buffer of the rank that OWNS the view
+ * (owner(v) = v / ceil(V / world)), into the slot of the sending rank -- peer memory over NVLink, overlapped with the
+ * gather itself.  After a barrier across the ranks (any collective on the same streams) every owner adds its `world`
+ * slots in rank order: the reduce-scatter-by-view a view-parallel 2D backbone consumes, deterministic.
+ *   d3m_p2p_*                   staging memory: cudaMalloc + CUDA IPC handle (64 bytes, exchanged by the caller's process
+ *                               group), opened once per peer.
+ *   d3m_back_project_bwd_exchange   as d3m_back_project_bwd, but grad goes to peer_staging_host[owner] (host array of
+ *                               `world` device pointers; entry `rank` is this rank's own buffer).  Staging layout of one
+ *                               rank: (world, ceil(V/world), B, H, W, C) float32, channels-last.
+ *   d3m_grad_slots_sum          owner side: out (n_views, B, C, H, W) = sum over the `world` slots, ascending rank order.
+ * ------------------------------------------------------------------------------------------- */
+int d3m_p2p_alloc(size_t bytes, void** dev_ptr, unsigned char* handle64_host);
+int d3m_p2p_open(const unsigned char* handle64_host, void** dev_ptr);
+int d3m_p2p_close(void* dev_ptr);
+int d3m_p2p_free(void* dev_ptr);
+int d3m_back_project_bwd_exchange(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                  float voxel_size, int V, int C, int H, int W, const float* KRcam,
+                                  const float* grad_out, const float* count, int* cell_hist,
+                                  void* const* peer_staging_host, int world, int rank, void* workspace,
+                                  size_t workspace_bytes, void* stream);
+int d3m_grad_slots_sum(const float* staging, int world, int views_per_owner, int n_views, int B, int C, int H, int W,
+                       float* out_nchw, void* stream);
+/* All-gather of per-voxel rows (view counts / occupancy for the next coarse-to-fine level, neucon_network.py:132,180-196)
+ * as peer stores: this rank's n_local rows of row_bytes bytes go into EVERY rank's full buffer (peer_dst_dev_table: DEVICE
+ * array of `world` device pointers) at their global positions -- begin + i for contiguous ranges (block == 0), or the
+ * block-cyclic map ((i / block) * world + rank) * block + i % block.  Complete on every rank after the caller's next
+ * collective on the same streams. */
+int d3m_p2p_scatter_rows(const void* src, int64_t n_local, int row_bytes, int64_t begin, int64_t block,
+                         void* const* peer_dst_dev_table, int world, int rank, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * TSDF fusion  (replaces TSDFVolume, tsdf_volume.py:10-307, and TSDFVolumeTorch :485-574)

@@ -74,9 +74,10 @@ def _worker(rank, world, port, errq):
         # ---- view-owner exchange: every rank ends with the summed gradient of ITS views only -----------------------------
         if hasattr(shard, "back_project_voxel_sharded_view_owner"):
             f2 = t(inp["feats"]).requires_grad_(True)
-            vol2, cnt2, grad_fn = shard.back_project_voxel_sharded_view_owner(
-                t(inp["coords"][b:e]), t(inp["origin"]), inp["voxel_size"], f2, t(inp["KRcam"]))
+            vol2, cnt2, grad_fn, full2 = shard.back_project_voxel_sharded_view_owner(
+                t(inp["coords"][b:e]), t(inp["origin"]), inp["voxel_size"], f2, t(inp["KRcam"]), count_rows=(N, b, 0))
             assert torch.equal(cnt2, cnt) and torch.equal(vol2, vol.detach())
+            assert torch.equal(full2, ref_cnt), "view counts all-gathered as peer stores != unsharded count"
             g_own, (v0, v1) = grad_fn(t(inp["grad_out"][b:e]))
             assert_close(g_own.cpu().numpy(), ref_feats.grad[v0:v1].cpu().numpy(), "owned view range of grad_feats")
 
