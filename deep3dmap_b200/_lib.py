@@ -18,7 +18,7 @@ SYMBOLS = (
     "d3m_back_project_fwd_partial", "d3m_back_project_fwd_finish",
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
     "d3m_p2p_alloc", "d3m_p2p_open", "d3m_p2p_close", "d3m_p2p_free", "d3m_back_project_bwd_exchange", "d3m_grad_slots_sum",
-    "d3m_p2p_scatter_rows",
+    "d3m_p2p_scatter_rows", "d3m_p2p_sync_mailbox_bytes", "d3m_p2p_sync",
     "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_device", "d3m_tsdf_reset", "d3m_tsdf_rebase", "d3m_tsdf_integrate_host",
     "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches", "d3m_upload",
     # ground-truth side of the dataloader transform
@@ -94,6 +94,10 @@ def lib():
     L.d3m_grad_slots_sum.restype = i32
     L.d3m_p2p_scatter_rows.argtypes = [vp, i64, i32, i64, i64, vp, i32, i32, vp]
     L.d3m_p2p_scatter_rows.restype = i32
+    L.d3m_p2p_sync_mailbox_bytes.argtypes = [i32]
+    L.d3m_p2p_sync_mailbox_bytes.restype = sz
+    L.d3m_p2p_sync.argtypes = [vp, i32, i32, ctypes.c_ulonglong, vp, i32, vp, vp]
+    L.d3m_p2p_sync.restype = i32
     L.d3m_tsdf_create.argtypes = [i32, i32, i32, vp, f32, f32, i32, ctypes.POINTER(vp)]
     L.d3m_tsdf_create.restype = i32
     L.d3m_tsdf_create_slab.argtypes = [i32, i32, i32, i32, vp, f32, f32, i32, ctypes.POINTER(vp)]

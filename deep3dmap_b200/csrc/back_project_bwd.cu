@@ -709,6 +709,7 @@ static int bwd_impl(const void* coords, int coords_kind, int64_t N, const float*
               D3M_ERR_ALIGN, "back_project backward: coords/KRcam/grad_feats/cell_hist/workspace must be 16-byte aligned");
   D3M_REQUIRE(workspace_bytes >= w.total, D3M_ERR_WORKSPACE, "back_project backward: workspace %zu < %zu",
               workspace_bytes, w.total);
+  PdlScope pdl_scope(stream, (long long)N * V);
   unsigned char* ws = static_cast<unsigned char*>(workspace);
   const bool own_state = cell_hist == nullptr;
   const BinState bins = bin_state(own_state ? reinterpret_cast<int*>(ws + w.state) : cell_hist, w.bl);

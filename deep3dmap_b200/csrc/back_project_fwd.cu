@@ -623,6 +623,37 @@ __global__ void __launch_bounds__(256) bp_prep_kernel(const float* __restrict__ 
   }
 }
 
+// Register-transpose variant for C % 4 == 0 and H*W % 4 == 0 (every NeuralRecon level): a thread loads four 128-bit pixel
+// quads of four consecutive channels, transposes the 4x4 block in registers and stores four 128-bit channel quads -- no
+// shared memory, no barrier, every store instruction of a warp covers whole 32-byte sectors (a pixel's C floats are
+// contiguous).  thread <-> (map, pixel quad, channel quad), channel quad fastest.
+__global__ void __launch_bounds__(256) bp_prep4_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int C4,
+                                                       int HW4, int64_t total, uint32_t* __restrict__ zero_ptr,
+                                                       int64_t zero_words) {
+  pdl_enter();
+  const int64_t nthreads = (int64_t)gridDim.x * 256;
+  const int64_t t0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (zero_words > 0) {
+    const int64_t nv = zero_words >> 2;
+    uint4* v = reinterpret_cast<uint4*>(zero_ptr);
+    for (int64_t i = t0; i < nv; i += nthreads) v[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (t0 < (zero_words & 3)) zero_ptr[(nv << 2) + t0] = 0u;
+  }
+  for (int64_t t = t0; t < total; t += nthreads) {
+    const int cq = (int)(t % C4);
+    const int64_t r = t / C4;
+    const int pq = (int)(r % HW4);
+    const int64_t m = r / HW4;
+    const float4* s = src + (m * (4 * C4) + 4 * cq) * HW4 + pq;   // channel 4cq of map m, pixel quad pq
+    const float4 a = __ldg(s), b = __ldg(s + HW4), c = __ldg(s + 2 * (int64_t)HW4), d = __ldg(s + 3 * (int64_t)HW4);
+    float4* o = dst + (m * (4 * (int64_t)HW4) + 4 * pq) * C4 + cq;  // pixel 4pq of map m, channel quad cq
+    o[0] = make_float4(a.x, b.x, c.x, d.x);
+    o[C4] = make_float4(a.y, b.y, c.y, d.y);
+    o[2 * C4] = make_float4(a.z, b.z, c.z, d.z);
+    o[3 * C4] = make_float4(a.w, b.w, c.w, d.w);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -773,6 +804,17 @@ static int launch_prep(const float* src_nchw, float* dst_nhwc, int64_t n_maps, i
     D3M_CUDA_CHECK(cudaGetLastError());
     return D3M_OK;
   }
+  static const bool use4 = env_int("D3M_PREP4", 1) != 0;
+  if (use4 && (C & 3) == 0 && (HW & 3) == 0 && aligned16(src_nchw) && aligned16(dst_nhwc)) {
+    const int64_t total = n_maps * (int64_t)(C / 4) * (HW / 4);
+    int64_t ctas = (total + 255) / 256;
+    if (ctas > 148 * 32) ctas = 148 * 32;
+    LaunchScope ls("bp_prep", stream);
+    launch_k(bp_prep4_kernel, dim3((unsigned)ctas), dim3(256), 0, stream, reinterpret_cast<const float4*>(src_nchw),
+             reinterpret_cast<float4*>(dst_nhwc), C / 4, HW / 4, total, zero_ptr, zero_words);
+    D3M_CUDA_CHECK(cudaGetLastError());
+    return D3M_OK;
+  }
   for (int64_t m0 = 0; m0 < n_maps; m0 += 65535) {
     const unsigned nz = (unsigned)((n_maps - m0) < 65535 ? (n_maps - m0) : 65535);
     dim3 grid((HW + 31) / 32, (C + 31) / 32, nz);
@@ -860,6 +902,7 @@ static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float*
   int rc = fwd_check(coords, coords_kind, N, origin, B, feats, feats_layout, feats_nhwc_scratch, V, C, H, W, KRcam, out,
                      count, workspace, workspace_bytes);
   if (rc != D3M_OK) return rc;
+  PdlScope pdl_scope(stream, (long long)N * V);
   BinLayout bl;
   memset(&bl, 0, sizeof(bl));
   if (cell_hist) {

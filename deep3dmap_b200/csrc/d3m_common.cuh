@@ -67,7 +67,16 @@ struct DeviceGuard {
 // Without the launch attribute (plain <<< >>>, D3M_PDL=0, or a memset / torch op in between) both instructions are no-ops
 // and the stream serialises as usual.  Works in eager streams and inside CUDA-graph capture (programmatic edges).
 // ------------------------------------------------------------------------------------------------
-bool pdl_enabled();  // core.cu: env D3M_PDL != "0"
+bool pdl_enabled();  // core.cu: D3M_PDL = 0 / 1, or (default) the decision of the enclosing PdlScope
+
+// Per-call decision of the default mode: chained launches only for calls small enough to be launch-latency bound
+// (voxel-view samples <= kPdlMaxWorkItems) and only outside CUDA-graph capture (see core.cu for the measurements).
+constexpr long long kPdlMaxWorkItems = 4ll << 20;
+struct PdlScope {
+  PdlScope(cudaStream_t stream, long long work_items);
+  ~PdlScope();
+  bool prev_;
+};
 
 __device__ __forceinline__ void pdl_enter() {
   asm volatile("griddepcontrol.wait;" ::: "memory");

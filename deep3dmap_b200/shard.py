@@ -217,40 +217,17 @@ class GradExchange:
         self.v1 = min(self.V, self.v0 + self.vpo)
         self.slot_floats = self.vpo * self.B * self.H * self.W * self.C
         nbytes = 4 * self.world * self.slot_floats
-        L = _lib.lib()
-        self._own, self._peers, self.tables = [], [], []
+        self._own, self.tables = [], []
         for _ in range(2):
-            ptr = ctypes.c_void_p()
-            handle = (ctypes.c_ubyte * 64)()
-            with voxel._on_device(device):
-                _lib.check(L.d3m_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "d3m_p2p_alloc")
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
-            ptrs = []
-            for r in range(self.world):
-                if r == self.rank:
-                    ptrs.append(ptr.value)
-                    continue
-                q = ctypes.c_void_p()
-                h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
-                with voxel._on_device(device):
-                    _lib.check(L.d3m_p2p_open(h, ctypes.byref(q)), "d3m_p2p_open (rank %d)" % r)
-                ptrs.append(q.value)
-                self._peers.append(q.value)
-            self._own.append(ptr.value)
+            own, ptrs = _p2p_buffers(nbytes, device, group)
+            self._own.append(own)
             self.tables.append((ctypes.c_void_p * self.world)(*ptrs))
         self._turn = 0
-        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
 
     def next_table(self):
         k = self._turn
         self._turn ^= 1
         return k, self.tables[k]
-
-    def barrier(self):
-        """All ranks' gather kernels issued before this call have completed (their peer stores have landed) once the
-        current stream passes this point: a 4-byte all-reduce ordered on the stream."""
-        dist.all_reduce(self._flag, group=self.group)
 
     def sum_slots(self, k):
         """-> (v1 - v0, B, C, H, W) gradient of this rank's views: its `world` slots added in ascending rank order."""
@@ -273,6 +250,83 @@ class _DevView:
         self._owner = owner
 
 
+def _p2p_buffers(nbytes, device, group, zero=False):
+    """One IPC-shared cudaMalloc buffer per rank, mapped everywhere: -> (own pointer, [pointer of rank 0..W-1])."""
+    import ctypes
+    rank, world = _world(group)
+    L = _lib.lib()
+    ptr = ctypes.c_void_p()
+    handle = (ctypes.c_ubyte * 64)()
+    with voxel._on_device(device):
+        _lib.check(L.d3m_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "d3m_p2p_alloc")
+    if zero:
+        torch.as_tensor(_DevView(ptr.value, (nbytes,), "|u1", None), device=device).zero_()
+        torch.cuda.synchronize(device)
+    handles = [None] * world
+    dist.all_gather_object(handles, bytes(handle), group=group)   # also orders the zero-fill before any peer's first write
+    ptrs = []
+    for r in range(world):
+        if r == rank:
+            ptrs.append(ptr.value)
+            continue
+        q = ctypes.c_void_p()
+        h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
+        with voxel._on_device(device):
+            _lib.check(L.d3m_p2p_open(h, ctypes.byref(q)), "d3m_p2p_open (rank %d)" % r)
+        ptrs.append(q.value)
+    return ptr.value, ptrs
+
+
+class PeerSync:
+    """All-reduce of a few doubles + barrier across the ranks of the box through peer memory (`d3m_p2p_sync`): the
+    exchange steps of the voxel-sharded path need nothing else, so a step issues no NCCL call at all.
+    `D3M_SHARD_SYNC=nccl` switches back to `dist.all_reduce` (A/B aid)."""
+
+    _cache = {}
+
+    @classmethod
+    def get(cls, device, group=None):
+        key = (device.index, id(group))
+        ps = cls._cache.get(key)
+        if ps is None:
+            ps = cls._cache[key] = cls(device, group)
+        return ps
+
+    def __init__(self, device, group=None):
+        self.device, self.group = device, group
+        self.rank, self.world = _world(group)
+        self.use_nccl = os.environ.get("D3M_SHARD_SYNC", "p2p") == "nccl"
+        self.epoch = 0
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+        if not self.use_nccl:
+            nbytes = _lib.lib().d3m_p2p_sync_mailbox_bytes(self.world)
+            self._own, ptrs = _p2p_buffers(nbytes, device, group, zero=True)
+            self._table = torch.tensor(ptrs, dtype=torch.int64, device=device)
+
+    def all_reduce_(self, sums):
+        """In-place sum of a small float64 tensor over the ranks (ascending rank order); doubles as the barrier."""
+        if self.use_nccl:
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=self.group)
+            return sums
+        self.epoch += 1
+        n = sums.numel()
+        with voxel._on_device(self.device):
+            rc = _lib.lib().d3m_p2p_sync(self._table.data_ptr(), self.world, self.rank, self.epoch, voxel._ptr(sums), n,
+                                         voxel._ptr(sums), voxel._stream(self.device))
+        _lib.check(rc, "d3m_p2p_sync")
+        return sums
+
+    def barrier(self):
+        if self.use_nccl:
+            dist.all_reduce(self._flag, group=self.group)
+            return
+        self.epoch += 1
+        with voxel._on_device(self.device):
+            rc = _lib.lib().d3m_p2p_sync(self._table.data_ptr(), self.world, self.rank, self.epoch, None, 0, None,
+                                         voxel._stream(self.device))
+        _lib.check(rc, "d3m_p2p_sync")
+
+
 class RowsExchange:
     """All-gather of per-voxel float32 rows (view counts, occupancy) as peer stores instead of a collective: every rank
     owns a full-size (n_total, width) buffer in IPC-shared memory and writes its rows straight into every rank's buffer at
@@ -293,30 +347,14 @@ class RowsExchange:
         import ctypes
         self.n_total, self.width, self.device, self.group = int(n_total), int(width), device, group
         self.rank, self.world = _world(group)
-        L = _lib.lib()
         nbytes = max(16, 4 * self.n_total * self.width)
         self._own, self._tables, self._views = [], [], []
         for _ in range(2):
-            ptr = ctypes.c_void_p()
-            handle = (ctypes.c_ubyte * 64)()
-            with voxel._on_device(device):
-                _lib.check(L.d3m_p2p_alloc(nbytes, ctypes.byref(ptr), handle), "d3m_p2p_alloc")
-            handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
-            ptrs = []
-            for r in range(self.world):
-                if r == self.rank:
-                    ptrs.append(ptr.value)
-                    continue
-                q = ctypes.c_void_p()
-                h = (ctypes.c_ubyte * 64).from_buffer_copy(handles[r])
-                with voxel._on_device(device):
-                    _lib.check(L.d3m_p2p_open(h, ctypes.byref(q)), "d3m_p2p_open (rank %d)" % r)
-                ptrs.append(q.value)
-            self._own.append(ptr.value)
+            own, ptrs = _p2p_buffers(nbytes, device, group)
+            self._own.append(own)
             self._tables.append(torch.tensor(ptrs, dtype=torch.int64, device=device))   # device-side pointer table
             shape = (self.n_total, self.width) if self.width > 1 else (self.n_total,)
-            self._views.append(torch.as_tensor(_DevView(ptr.value, shape, "<f4", self), device=device))
+            self._views.append(torch.as_tensor(_DevView(own, shape, "<f4", self), device=device))
         self._turn = 0
 
     def scatter(self, local, begin=0, block=0):
@@ -355,7 +393,7 @@ def back_project_voxel_sharded_view_owner(coords_local, origin, voxel_size, feat
             full_count = count
     if world > 1:
         # 3 fp64 scalars per fragment -- and the barrier after which every rank's count rows have landed
-        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        PeerSync.get(out.device, group).all_reduce_(sums)
     out = ops.forward_finish(out, sums, state)
     _, _, (V, B, H, W, C), coords, origin_d, KR, hist = state
     dev = out.device
@@ -376,7 +414,7 @@ def back_project_voxel_sharded_view_owner(coords_local, origin, voxel_size, feat
                 voxel._ptr(KR), voxel._ptr(g), voxel._ptr(count), voxel._ptr(hist), table, world, rank, ws.data_ptr(),
                 ws_bytes, voxel._stream(dev))
         _lib.check(rc, "d3m_back_project_bwd_exchange")
-        ex.barrier()
+        PeerSync.get(dev, group).barrier()      # every rank's gather has finished: all slots of this rank are complete
         return ex.sum_slots(k), (ex.v0, ex.v1)
 
     if count_rows is not None:

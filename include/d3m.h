@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 108
+#define D3M_VERSION 109
 
 enum {
   D3M_OK = 0,
@@ -173,6 +173,14 @@ int d3m_grad_slots_sum(const float* staging, int world, int views_per_owner, int
  * collective on the same streams. */
 int d3m_p2p_scatter_rows(const void* src, int64_t n_local, int row_bytes, int64_t begin, int64_t block,
                          void* const* peer_dst_dev_table, int world, int rank, void* stream);
+/* All-reduce (sum, ascending rank order) of n <= 192 doubles AND barrier across the ranks of one box through peer memory:
+ * one small kernel per rank writes its payload + a flag (`epoch`, the caller's call counter, > 0 and equal on all ranks)
+ * into every rank's mailbox and waits for the others' flags.  Peer stores of earlier kernels on the same stream (count
+ * rows, gradient slots) have arrived wherever the flag has.  mailbox_dev_table: DEVICE array of `world` pointers to the
+ * ranks' mailboxes (d3m_p2p_sync_mailbox_bytes(world) bytes each, zero-filled once).  n == 0: barrier only. */
+size_t d3m_p2p_sync_mailbox_bytes(int world);
+int d3m_p2p_sync(void* const* mailbox_dev_table, int world, int rank, unsigned long long epoch, const double* payload, int n,
+                 double* out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * TSDF fusion  (replaces TSDFVolume, tsdf_volume.py:10-307, and TSDFVolumeTorch :485-574)
