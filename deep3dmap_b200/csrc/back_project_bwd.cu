@@ -579,9 +579,7 @@ static void pick_gather_tile(int C, int& TX, int& TY, size_t& smem) {
 template <int KIND>
 static int launch_bwd(BwdParams p, const BinState& bins, const BinLayout& bl, bool own_state, float* cnt_ws,
                       cudaStream_t stream) {
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int sms = current_device_sms();
   const unsigned vox_ctas = (unsigned)((p.N + kSampleThreads - 1) / kSampleThreads);
   const unsigned vgroups = (unsigned)((p.V + kViewsPerThread - 1) / kViewsPerThread);
   if (cnt_ws) {  // no forward count handed over: recompute it
@@ -632,7 +630,7 @@ static int launch_bwd(BwdParams p, const BinState& bins, const BinLayout& bl, bo
     const int64_t tiles = (int64_t)p.V * p.B * tiles_x * tiles_y;
     D3M_REQUIRE(tiles < (1ll << 31), D3M_ERR_ARG, "back_project backward: too many gather tiles");
     smem += (size_t)kGatherWarps * 4 * p.C * 4;  // scratch of the cooperative big-cell pass
-    D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    D3M_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem));
     LaunchScope ls("bp_bwd_gather", stream);
     launch_k(k, dim3((unsigned)tiles), dim3(kGatherWarps * 32), smem, stream, p, TX, TY, tiles_x, tiles_y);
     D3M_CUDA_CHECK(cudaGetLastError());

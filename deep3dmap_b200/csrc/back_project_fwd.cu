@@ -309,6 +309,134 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
   if (p.fuse_stats) fused_stats_finish(p, lane, warp);
 }
 
+// ---- 256-bit variant (C % 8 == 0): a lane owns R groups of EIGHT consecutive channels and fetches each corner of a texel
+// with one LDG.E.256 (sm_100: ld.global.v8.f32; a texel is C*4 = 96 / 160 / 320 bytes = 3 / 5 / 10 x 32 bytes and starts on
+// a 32-byte boundary).  Half the load instructions of the 128-bit kernel for the same bytes, and twice as many voxels per
+// lane-group round (G lanes per voxel instead of 2G).  Same arithmetic per channel, hence the same bits.
+struct F8 { float v[8]; };
+__device__ __forceinline__ F8 ldg256(const float* p) {
+  F8 r;
+  asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+
+template <int KIND, int G, int R>
+__global__ void __launch_bounds__(kFwdWarps * 32, 6) bp_fwd8_kernel(const FwdParams p) {
+  pdl_enter();
+  extern __shared__ __align__(16) unsigned char smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int NG = 32 / G;  // lane groups per warp
+  const int g = lane / G, gl = lane % G;
+  const int C = p.C, C1 = C + 1;
+  unsigned char* wbase = smem + (size_t)warp * p.per_warp_bytes;
+  float* outs = reinterpret_cast<float*>(wbase);  // (tv, C+1), 16-byte aligned start
+  int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
+  float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
+  float* rec_fy = rec_fx + p.vchunk * 32;
+
+  for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
+       tile += (int64_t)gridDim.x * kFwdWarps) {
+    const int64_t n0 = tile * p.tv;
+    const int64_t n = n0 + lane;
+    const bool active = lane < p.tv && n < p.N;
+    int b = -1;
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    if (active) {
+      float cx, cy, cz;
+      b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
+      if (b >= 0) {
+        const float* o = p.origin + 3 * b;
+        voxel_world(cx, cy, cz, p.vs, __ldg(o), __ldg(o + 1), __ldg(o + 2), gx, gy, gz);
+      }
+    }
+    int cnt = 0;
+    float zsum = 0.0f;
+    for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
+      const int v1 = min(p.V, v0 + p.vchunk);
+      const bool first = (v0 == 0), last = (v1 == p.V);
+      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      cnt += ccnt;
+      __syncwarp();
+      for (int r = 0; r * NG < p.tv; ++r) {
+        const int j = r * NG + g;
+        const bool gvalid = (g < NG) && (j < p.tv);
+        int cj = __shfl_sync(kFull, ccnt, gvalid ? j : 0);
+        const int ctot = __shfl_sync(kFull, cnt, gvalid ? j : 0);
+        if (!gvalid) cj = 0;
+        const int kmax = __reduce_max_sync(kFull, cj);
+        float acc[R][8];
+#pragma unroll
+        for (int i = 0; i < R; ++i) {
+          const float* q = outs + j * C1 + (i * G + gl) * 8;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[i][e] = (first || !gvalid) ? 0.0f : q[e];
+        }
+#pragma unroll 1
+        for (int k = 0; k < kmax; ++k) {
+          const bool on = k < cj;
+          const int jj = on ? j : 0;
+          const int of = rec_off[k * 32 + jj];
+          const float fx = on ? rec_fx[k * 32 + jj] : 0.0f, fy = on ? rec_fy[k * 32 + jj] : 0.0f;
+          const bool x1 = on && (of & kFlagX1), y1 = on && (of & kFlagY1);
+          const float wx0 = __fsub_rn(1.0f, fx), wy0 = __fsub_rn(1.0f, fy);
+          const float nw = __fmul_rn(wx0, wy0), ne = __fmul_rn(fx, wy0), sw = __fmul_rn(wx0, fy),
+                      se = __fmul_rn(fx, fy);
+          const float* base = p.feats + (int64_t)(of & kOffMask) * C + gl * 8;
+          F8 t00[R], t01[R], t10[R], t11[R];
+          F8 zero;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) zero.v[e] = 0.0f;
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            t00[i] = on ? ldg256(base + i * G * 8) : zero;
+            t01[i] = x1 ? ldg256(base + C + i * G * 8) : zero;
+            t10[i] = y1 ? ldg256(base + (int64_t)p.W * C + i * G * 8) : zero;
+            t11[i] = (x1 && y1) ? ldg256(base + (int64_t)(p.W + 1) * C + i * G * 8) : zero;
+          }
+#pragma unroll
+          for (int i = 0; i < R; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              acc[i][e] = __fadd_rn(acc[i][e], corner_chain(t00[i].v[e], t01[i].v[e], t10[i].v[e], t11[i].v[e], nw, ne, sw, se));
+        }
+        if (gvalid) {
+          const float div = (float)max(ctot, 1);
+#pragma unroll
+          for (int i = 0; i < R; ++i) {
+            float* q = outs + j * C1 + (i * G + gl) * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) q[e] = last ? __fdiv_rn(acc[i][e], div) : acc[i][e];   // back_project.py:69-72
+          }
+        }
+      }
+      __syncwarp();
+    }
+    // per-voxel scalars: count, mean depth (normalised later), fragment index
+    if (lane < p.tv) {
+      const float zb = __fdiv_rn(zsum, (float)max(cnt, 1));
+      outs[lane * C1 + C] = zb;
+      if (active) {
+        p.count[n] = (float)cnt;
+        p.zbar[n] = zb;
+        p.bidx[n] = b;
+      }
+    }
+    const int rows = (int)min((int64_t)p.tv, p.N - n0);
+    const int bytes = rows * C1 * 4;
+    float* gdst = p.out + n0 * C1;
+    if ((bytes & 15) == 0) {
+      bulk_store_tile(gdst, outs, bytes, lane);
+    } else {
+      __syncwarp();
+      for (int i = lane; i < rows * C1; i += 32) gdst[i] = outs[i];
+      __syncwarp();
+    }
+  }
+  if (p.fuse_stats) fused_stats_finish(p, lane, warp);
+}
+
 // Any channel count up to 256: the warp takes one voxel at a time, lanes stride over channels (scalar loads).
 constexpr int kGenericMaxR = 8;
 template <int KIND>
@@ -695,6 +823,11 @@ static FwdWs fwd_ws_layout(int64_t N, int B) {
 
 typedef void (*fwd_kernel_t)(const FwdParams);
 
+static int env_int_early(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : dflt;
+}
+
 // (G lanes x R float4 per lane) = C/4 channel quads per voxel.  The table lists every instantiated shape; for a given
 // C the FIRST matching row is the default, D3M_FWD_GR="C:G:R[,C:G:R...]" (tuning aid) selects another one.
 template <int KIND>
@@ -710,6 +843,16 @@ static fwd_kernel_t pick_fwd_kernel(int C, int& G, int& R) {
 #undef D3M_FWD_ROW
   G = 0; R = 0;
   if (C % 4 != 0) return nullptr;
+  static const int w8 = env_int_early("D3M_FWD_W8", 0);   // 256-bit texel loads (C % 8 == 0)
+  if (w8 && C % 8 == 0) {
+    struct Row8 { int g, r; fwd_kernel_t k; };
+#define D3M_FWD8_ROW(g, r) {g, r, bp_fwd8_kernel<KIND, g, r>}
+    static const Row8 rows8[] = {D3M_FWD8_ROW(3, 1), D3M_FWD8_ROW(5, 1), D3M_FWD8_ROW(10, 1), D3M_FWD8_ROW(5, 2),
+                                 D3M_FWD8_ROW(2, 1), D3M_FWD8_ROW(4, 1), D3M_FWD8_ROW(8, 1), D3M_FWD8_ROW(16, 1)};
+#undef D3M_FWD8_ROW
+    for (const Row8& row : rows8)
+      if (row.g * row.r == C / 8 && !(w8 == 2 && C == 80 && row.g == 10)) { G = row.g; R = row.r; return row.k; }
+  }
   const int q = C / 4;
   int want_g = 0, want_r = 0;
   if (const char* env = getenv("D3M_FWD_GR")) {
@@ -746,9 +889,7 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream, int* grid_out, i
                 32 * kGenericMaxR);
     k = bp_fwd_generic_kernel<KIND>;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int sms = current_device_sms();
   if (sms > kFwdMaxSms) sms = kFwdMaxSms;
   // Launch shape.  Large N: 32-voxel warp tiles, grid capped at 32 CTAs per SM (grid-stride).  Small N (the launch is a
   // single wave): the kernel's duration is ONE warp's chain -- views x projection, then tile/NG rounds of count[n] dependent
@@ -771,7 +912,7 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream, int* grid_out, i
   p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)3 * p.vchunk * 32 * 4, 16);
   const size_t smem = (size_t)p.per_warp_bytes * kFwdWarps;
   D3M_REQUIRE(smem <= 200 * 1024, D3M_ERR_ARG, "back_project: C=%d needs %zu B shared memory per CTA", p.C, smem);
-  D3M_CUDA_CHECK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  D3M_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem));
   int64_t ctas = (p.num_tiles + kFwdWarps - 1) / kFwdWarps;
   const int64_t cap = (int64_t)sms * kFwdMaxCtasPerSm;
   if (ctas > cap) ctas = cap;

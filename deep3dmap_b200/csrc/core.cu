@@ -56,6 +56,35 @@ PdlScope::PdlScope(cudaStream_t stream, long long work_items) : prev_(g_pdl_call
 }
 PdlScope::~PdlScope() { g_pdl_call = prev_; }
 
+int current_device_sms() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64) {
+    const int c = cache[dev].load(std::memory_order_relaxed);
+    if (c > 0) return c;
+  }
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < 64) cache[dev].store(sms, std::memory_order_relaxed);
+  return sms;
+}
+
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes) {
+  // the attribute is per (function, device); remember the largest value set so far
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> set;
+  if (bytes <= 48 * 1024) return cudaSuccess;   // the default limit needs no opt-in
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lk(mu);
+  size_t& cur = set[{kernel, dev}];
+  if (bytes <= cur) return cudaSuccess;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess) cur = bytes;
+  return e;
+}
+
 static std::atomic<long long> g_launches{0};
 static std::atomic<bool> g_profiling{false};
 static std::mutex g_prof_mu;

@@ -99,6 +99,10 @@ static inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 blo
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// host-side caches of things every call used to ask the driver (an eager fragment step is host-bound):
+int current_device_sms();                                  // SM count of the current device
+cudaError_t ensure_dynamic_smem(const void* kernel, size_t bytes);  // cudaFuncSetAttribute only when the need grows
+
 // zero-fill on the stream: a PDL-chained kernel (core.cu) when it can be, cudaMemsetAsync otherwise
 int zero_async(void* p, size_t bytes, cudaStream_t stream);
 

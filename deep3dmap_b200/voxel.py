@@ -155,6 +155,19 @@ def back_project_forward(coords, origin, voxel_size, feats, KRcam, cell_hist=Fal
     """Kernel-level forward.  `feats`: channels-last maps (V,B,H,W,C), or with nchw=True the reference layout (V,B,C,H,W)
     (re-laid out by the same launch that clears the binning state).  Returns (volume (N,C+1), count (N,)) and, with
     cell_hist=True, additionally the int32 binning state the backward pass starts from."""
+    out, count, buf, off = _forward_raw(coords, origin, voxel_size, feats, KRcam, cell_hist, nchw)
+    if not cell_hist:
+        return out, count
+    if buf is None:
+        V, B = KRcam.shape[0], KRcam.shape[1]
+        H, W = (feats.shape[3], feats.shape[4]) if nchw else (feats.shape[2], feats.shape[3])
+        return out, count, _new_cell_hist(coords.shape[0], B, V, H, W, feats.device)
+    return out, count, buf[off:].view(torch.int32)
+
+
+def _forward_raw(coords, origin, voxel_size, feats, KRcam, cell_hist, nchw):
+    """-> (out, count, buf, state_offset): `buf` = the call's workspace with the binning state at byte `state_offset`
+    (None for an empty voxel list)."""
     L = _lib.lib()
     dev = feats.device
     if nchw:
@@ -166,19 +179,22 @@ def back_project_forward(coords, origin, voxel_size, feats, KRcam, cell_hist=Fal
         raise ValueError("origin must be (B,3) and KRcam (V,B,4,4) for feats (V,B,C,H,W)")
     out = torch.empty((N, C + 1), dtype=torch.float32, device=dev)
     count = torch.empty((N,), dtype=torch.float32, device=dev)
-    hist = None
-    if cell_hist:
-        hist = _new_cell_hist(N, B, V, H, W, dev)
+    buf, ws_bytes = None, 0
     if N > 0:
         scratch = torch.empty((V, B, H, W, C), dtype=torch.float32, device=dev) if nchw else None
-        ws, ws_bytes = _workspace("f", (N, B, V, C), dev)
+        # ONE allocation for the call's workspace and, behind it, the binning state handed to backward (an eager
+        # fragment-sized step is host-bound: every torch.empty is ~3 us)
+        ws_bytes = _memo(("f", N, B, V, C), lambda: (L.d3m_back_project_fwd_workspace(N, B, V, C) + 255) // 256 * 256)
+        hist_elems = _memo(("h", N, B, V, H, W), lambda: L.d3m_back_project_cell_hist_elems(N, B, V, H, W)) if cell_hist else 0
+        buf = torch.empty((ws_bytes + 4 * hist_elems,), dtype=torch.uint8, device=dev)
+        hist_ptr = buf.data_ptr() + ws_bytes if cell_hist else None
         with _on_device(dev):
             rc = L.d3m_back_project_fwd(coords.data_ptr(), _COORD_KIND[coords.dtype], N, origin.data_ptr(), B,
                                         float(voxel_size), feats.data_ptr(), _lib.FEATS_NCHW if nchw else _lib.FEATS_NHWC,
                                         _ptr(scratch), V, C, H, W, KRcam.data_ptr(), out.data_ptr(), count.data_ptr(),
-                                        _ptr(hist), ws.data_ptr(), ws_bytes, _stream(dev))
+                                        hist_ptr, buf.data_ptr(), ws_bytes, _stream(dev))
         _lib.check(rc, "d3m_back_project_fwd")
-    return (out, count, hist) if cell_hist else (out, count)
+    return out, count, buf, ws_bytes
 
 
 def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, grad_out, nchw=False, count=None,
@@ -204,7 +220,8 @@ def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, g
     ws, ws_bytes = _workspace("b", (N, B, V, C, H, W), dev)
     with _on_device(dev):
         rc = L.d3m_back_project_bwd(_ptr(coords), _COORD_KIND[coords.dtype], N, _ptr(origin), B, float(voxel_size),
-                                    V, C, H, W, _ptr(KRcam), _ptr(grad_out), _ptr(count), _ptr(cell_hist), grad.data_ptr(),
+                                    V, C, H, W, _ptr(KRcam), _ptr(grad_out), _ptr(count),
+                                    cell_hist if isinstance(cell_hist, int) else _ptr(cell_hist), grad.data_ptr(),
                                     1 if nchw else 0, ws.data_ptr(), ws_bytes, _stream(dev))
     _lib.check(rc, "d3m_back_project_bwd")
     return grad
@@ -221,12 +238,13 @@ class _BackProject(torch.autograd.Function):
         coords, origin, KRcam = _prep_small(coords, origin, KRcam, dev)
         store, layout = _feats_layout(feats)
         nchw = layout == _lib.FEATS_NCHW
-        if ctx.needs_input_grad[0]:
-            # backward will follow: let the forward pass, which projects every voxel anyway, histogram the samples
-            out, count, hist = back_project_forward(coords, origin, voxel_size, store, KRcam, cell_hist=True, nchw=nchw)
-            ctx.save_for_backward(coords, origin, KRcam, count, hist)
+        # when backward will follow, the forward pass -- which projects every voxel anyway -- also builds the binning state
+        want = bool(ctx.needs_input_grad[0])
+        out, count, buf, off = _forward_raw(coords, origin, voxel_size, store, KRcam, want, nchw)
+        ctx.state_off = off
+        if want and buf is not None:
+            ctx.save_for_backward(coords, origin, KRcam, count, buf)
         else:
-            out, count = back_project_forward(coords, origin, voxel_size, store, KRcam, nchw=nchw)
             ctx.save_for_backward(coords, origin, KRcam, count)
         V, B, C, H, W = feats.shape
         ctx.voxel_size = float(voxel_size)
@@ -239,7 +257,9 @@ class _BackProject(torch.autograd.Function):
     def backward(ctx, grad_vol, grad_count):
         if not ctx.needs_input_grad[0] or grad_vol is None:
             return None, None, None, None, None
-        coords, origin, KRcam, count, hist = ctx.saved_tensors
+        saved = ctx.saved_tensors
+        coords, origin, KRcam, count = saved[:4]
+        hist = saved[4].data_ptr() + ctx.state_off if len(saved) > 4 else None   # binning state behind the forward workspace
         g = grad_vol if (grad_vol.is_contiguous() and grad_vol.dtype == torch.float32) else grad_vol.contiguous().float()
         if GRAD_LAYOUT == "view":
             grad = back_project_backward(coords, origin, ctx.voxel_size, ctx.nhwc_shape, KRcam, g, count=count,
