@@ -9,7 +9,7 @@ and every compute call raises `D3MError` if it (or a CUDA device) is missing.
 from ._lib import D3MError, LIB_PATH  # noqa: F401
 
 __all__ = ["back_project", "TSDFVolume", "TSDFVolumeTorch", "get_view_frustum", "rigid_transform", "D3MError",
-           "SeqRandomTransformSpace"]
+           "SeqRandomTransformSpace", "marching_cubes"]
 
 
 def __getattr__(name):
@@ -20,6 +20,9 @@ def __getattr__(name):
     if name in ("TSDFVolume", "TSDFVolumeTorch", "get_view_frustum", "rigid_transform"):
         from . import tsdf
         return getattr(tsdf, name)
+    if name == "marching_cubes":
+        from .mesh import marching_cubes
+        return marching_cubes
     if name == "SeqRandomTransformSpace":
         from .transforms import SeqRandomTransformSpace
         return SeqRandomTransformSpace

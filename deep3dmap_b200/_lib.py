@@ -21,6 +21,7 @@ SYMBOLS = (
     "d3m_p2p_scatter_rows", "d3m_p2p_sync_mailbox_bytes", "d3m_p2p_sync",
     "d3m_tsdf_create", "d3m_tsdf_create_slab", "d3m_tsdf_destroy", "d3m_tsdf_device", "d3m_tsdf_reset", "d3m_tsdf_rebase", "d3m_tsdf_integrate_host",
     "d3m_tsdf_integrate_device", "d3m_tsdf_volumes", "d3m_tsdf_download", "d3m_tsdf_last_launches", "d3m_upload",
+    "d3m_mc_max_triangles_per_cube", "d3m_mc_flags", "d3m_mc_emit",
     # ground-truth side of the dataloader transform
     "d3m_tsdf_occupancy", "d3m_gt_recrop",
     # level glue around back_project
@@ -122,7 +123,10 @@ def lib():
     L.d3m_tsdf_last_launches.restype = i32
     L.d3m_upload.argtypes = [vp, vp, sz, vp]
     L.d3m_upload.restype = i32
+    L.d3m_mc_max_triangles_per_cube.restype = i32
     sigs = {
+        "d3m_mc_flags": [vp, i32, i32, i32, f32, vp, vp, vp],
+        "d3m_mc_emit": [vp, i32, i32, i32, f32, vp, i64, vp, i64, vp, vp, vp, vp, vp],
         "d3m_grid_coords": [i32, i32, i32, i32, i32, vp, vp, vp],
         "d3m_upsample": [vp, i32, vp, i64, i32, i32, i32, vp, vp, vp],
         "d3m_aligned_camera_coords": [vp, i32, i64, vp, i32, f32, vp, vp, vp],

@@ -9,7 +9,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["core.cu", "back_project_fwd.cu", "back_project_bwd.cu", "tsdf.cu", "level_glue.cu", "fusion.cu", "gt_crop.cu"]
+SOURCES = ["core.cu", "back_project_fwd.cu", "back_project_bwd.cu", "tsdf.cu", "level_glue.cu", "fusion.cu", "gt_crop.cu", "marching_cubes.cu"]
 LIB = os.path.join(HERE, "libd3m.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "--fmad=true"]
@@ -23,7 +23,10 @@ def _newer_than_lib(paths):
 
 
 def build(force=False, verbose=False):
+    from . import mc_tables
+    mc_tables.write_inc()          # generated case table of the marching-cubes kernels (rewritten only when it changes)
     deps = [os.path.join(CSRC, s) for s in SOURCES] + [os.path.join(CSRC, "d3m_common.cuh"),
+                                                       os.path.join(CSRC, "mc_tables.inc"),
                                                        os.path.join(os.path.dirname(HERE), "include", "d3m.h")]
     if not force and not _newer_than_lib(deps):
         return LIB

@@ -132,7 +132,7 @@ def save_tsdf_full(args, scene_path, cam_intr, depth_list, cam_pose_list, color_
     if save_mesh:
         for l in range(args.num_layers):
             print("Saving mesh to mesh{}.ply...".format(str(l)))
-            verts, faces, norms, colors = tsdf_vol_list[l].get_mesh()   # needs scikit-image, as in the reference
+            verts, faces, norms, colors = tsdf_vol_list[l].get_mesh()   # CUDA marching cubes (mesh.py)
             meshwrite(os.path.join(tsdf_path, 'mesh_layer{}.ply'.format(str(l))), verts, faces, norms, colors)
     return tsdf_vol_list
 

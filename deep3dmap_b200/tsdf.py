@@ -237,15 +237,22 @@ class TSDFVolume:
         _lib.check(_lib.lib().d3m_tsdf_reset(self._h.ptr, self._h.stream(self._stream)), "d3m_tsdf_reset")
 
     def _marching_cubes(self):
-        try:
-            from skimage import measure
-        except Exception as err:  # skimage is not part of this image
-            raise ImportError("get_mesh/get_point_cloud need scikit-image (marching cubes), as in the reference") from err
-        tsdf_vol, color_vol, weight_vol = self.get_volume()
-        fn = getattr(measure, "marching_cubes_lewiner", None) or measure.marching_cubes
-        verts, faces, norms, vals = fn(tsdf_vol, level=0)
+        """tsdf_volume.py:309-346: marching cubes at level 0 over the TSDF volume, vertices to world coordinates, vertex
+        colours unpacked from the colour volume.  The extraction runs on the volume where it lives (csrc/marching_cubes.cu
+        through `mesh.marching_cubes_device`; see mesh.py for the relation to scikit-image's variant)."""
+        import torch
+        from . import mesh
+        t_dev, _, _ = self._h.volumes()
+        hdev = torch.device("cuda", self._h.device)
+        st = self._h.stream(self._stream)
+        if st is not None and "torch" in sys.modules:
+            # the handle's stream may not be torch's current one: order the extraction after the integrations
+            torch.cuda.synchronize(hdev)
+        verts, faces, norms = mesh.marching_cubes_device(torch.as_tensor(t_dev, device=hdev), 0.0)
+        verts, faces, norms = verts.cpu().numpy(), faces.cpu().numpy(), norms.cpu().numpy()
+        _, color_vol, _ = self.get_volume()
         verts_ind = np.round(verts).astype(int)
-        verts = verts * self._voxel_size + self._vol_origin
+        verts = verts * self._voxel_size + self._vol_origin  # voxel grid coordinates to world coordinates
         rgb_vals = color_vol[verts_ind[:, 0], verts_ind[:, 1], verts_ind[:, 2]]
         colors_b = np.floor(rgb_vals / self._color_const)
         colors_g = np.floor((rgb_vals - colors_b * self._color_const) / 256)

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 109
+#define D3M_VERSION 110
 
 enum {
   D3M_OK = 0,
@@ -246,6 +246,25 @@ int d3m_tsdf_last_launches(d3m_tsdf* h);
  * while the previous chunk is in flight on the copy engine.  Returns when the last chunk is staged: `host_src` may be
  * reused at once, the data is in `dev_dst` for everything ordered after the call on `stream`. */
 int d3m_upload(const void* host_src, void* dev_dst, size_t bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Mesh export: marching cubes over a dense (X,Y,Z) float32 volume on the device (replaces the
+ * skimage.measure.marching_cubes[_lewiner](tsdf_vol, level=0) calls of tsdf_volume.py:315,335 and
+ * core/utils/neucon_utils.py:177).  Two passes around the ordered compaction d3m_compact:
+ *   d3m_mc_flags   edge_flags (X*Y*Z, 3) uint8: the edge leaving voxel v along +x/+y/+z crosses the level ("inside" = value
+ *                  < level); tri_flags (X*Y*Z, K) uint8, K = d3m_mc_max_triangles_per_cube(): slot k of the cube whose low
+ *                  corner is v holds a triangle
+ *   d3m_mc_emit    edge_list / tri_list = d3m_compact of those flags (int64, ascending); writes verts (n_verts,3) in voxel
+ *                  coordinates, unit normals (n_verts,3) pointing towards larger values, faces (n_faces,3) int32 vertex ids
+ *                  (counter-clockwise seen from the larger-value side), and edge_to_vertex (X*Y*Z*3 int32 scratch).
+ * Vertices are the level crossings of the grid edges (linear interpolation), shared between faces; the case table is
+ * generated by deep3dmap_b200/mc_tables.py (ambiguous faces always separate the inside corners: watertight).
+ * ------------------------------------------------------------------------------------------- */
+int d3m_mc_max_triangles_per_cube(void);
+int d3m_mc_flags(const float* volume, int X, int Y, int Z, float level, uint8_t* edge_flags, uint8_t* tri_flags, void* stream);
+int d3m_mc_emit(const float* volume, int X, int Y, int Z, float level, const int64_t* edge_list, int64_t n_verts,
+                const int64_t* tri_list, int64_t n_faces, int* edge_to_vertex, float* verts, float* normals, int* faces,
+                void* stream);
 
 /* =============================================================================================
  * SURVEY section 8 row f1, ground-truth side of the dataloader transform
