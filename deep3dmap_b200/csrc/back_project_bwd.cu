@@ -58,7 +58,7 @@ struct BwdParams {
   int xchg_rank, xchg_vpo;         // this rank; views per owner
   float* xchg_peer[kMaxExchangeRanks];  // staging buffer of every rank, (world, vpo, B, H, W, C), mapped in this process
   // fill + ghat launch
-  int fill_ctas_x, fill_ctas;      // voxel CTAs per view group; fill CTAs in total (the CTAs behind them write ghat)
+  int fill_ctas_x, ghat_ctas;      // voxel CTAs per view group of the fill pass; CTAs of the pre-division pass (they come first)
 };
 
 constexpr int kSampleThreads = 256;
@@ -184,18 +184,21 @@ __device__ __forceinline__ void ghat_rows(const BwdParams& p, const int64_t wg, 
   }
 }
 
-// ONE launch, two independent jobs: CTAs [0, fill_ctas) run the fill pass (CTA i <-> voxel block i % fill_ctas_x, view
-// group i / fill_ctas_x), the CTAs behind them the pre-division pass.
+// ONE launch, two independent jobs: CTAs [0, ghat_ctas) run the pre-division pass, the CTAs behind them the fill pass
+// (CTA j <-> voxel block j % fill_ctas_x, view group j / fill_ctas_x).
 template <int KIND>
 __global__ void __launch_bounds__(kSampleThreads) bp_bwd_fill_ghat_kernel(const BwdParams p) {
   pdl_enter();
+  // the streaming job first: its CTAs are dispatched together with the first fill CTAs, so that its DRAM traffic overlaps
+  // the fill pass's atomics instead of trailing it
   const int i = blockIdx.x;
-  if (i < p.fill_ctas) {
-    const int bx = i % p.fill_ctas_x, by = i / p.fill_ctas_x;
-    sample_pass<KIND, true>(p, (int64_t)bx * kSampleThreads + threadIdx.x, by * kViewsPerThread);
+  if (i < p.ghat_ctas) {
+    ghat_rows(p, (int64_t)i * (kSampleThreads / 32) + (threadIdx.x >> 5), threadIdx.x & 31);
     return;
   }
-  ghat_rows(p, (int64_t)(i - p.fill_ctas) * (kSampleThreads / 32) + (threadIdx.x >> 5), threadIdx.x & 31);
+  const int j = i - p.ghat_ctas;
+  const int bx = j % p.fill_ctas_x, by = j / p.fill_ctas_x;
+  sample_pass<KIND, true>(p, (int64_t)bx * kSampleThreads + threadIdx.x, by * kViewsPerThread);
 }
 
 // legacy path (no forward histogram): scan as a kernel of its own
@@ -253,6 +256,10 @@ __device__ __forceinline__ float4 add4(const float4 a, const float4 b) {
   return make_float4(__fadd_rn(a.x, b.x), __fadd_rn(a.y, b.y), __fadd_rn(a.z, b.z), __fadd_rn(a.w, b.w));
 }
 
+// Measured and dropped (profiles/r02x_step_variants.txt): a prologue that fetches every cell's [start, end) range and, if
+// they fit, the window's entries into shared memory (two parallel steps instead of a dependent chain per cell and round):
+// the extra barriers and the serial row bookkeeping cost more than the chain -- fragment level 2 50 -> 60-65 us, dense
+// level 2 113 -> 144 us.
 constexpr int kBigCell = 256;  // entries from which a cell is processed by the whole CTA instead of one lane group
 constexpr int kMaxBig = 64;    // deferred cells per tile (further ones are simply processed by their own group)
 
@@ -608,7 +615,7 @@ static int launch_bwd(BwdParams p, const BinState& bins, const BinLayout& bl, bo
     const int64_t fill_ctas = (int64_t)vox_ctas * vgroups;
     D3M_REQUIRE(fill_ctas + ghat_blocks < (1ll << 31), D3M_ERR_ARG, "back_project backward: too many fill CTAs");
     p.fill_ctas_x = (int)vox_ctas;
-    p.fill_ctas = (int)fill_ctas;
+    p.ghat_ctas = (int)ghat_blocks;
     LaunchScope ls("bp_bwd_fill_ghat", stream);
     launch_k(bp_bwd_fill_ghat_kernel<KIND>, dim3((unsigned)(fill_ctas + ghat_blocks)), dim3(kSampleThreads), 0, stream, p);
     D3M_CUDA_CHECK(cudaGetLastError());

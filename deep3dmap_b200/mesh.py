@@ -76,3 +76,51 @@ def marching_cubes(volume, level=0.0):
     verts, faces, normals = marching_cubes_device(vol, level)
     v = verts.cpu().numpy()
     return v, faces.cpu().numpy(), normals.cpu().numpy(), np.full((v.shape[0],), np.float32(level), dtype=np.float32)
+
+
+class TriMesh:
+    """The three arrays `SaveScene.tsdf2mesh` (neucon_utils.py:176-180) wraps in a `trimesh.Trimesh` (trimesh is not part
+    of this image): `vertices` (V,3) world coordinates, `faces` (F,3), `vertex_normals` (V,3); `export(path)` writes the
+    binary little-endian .ply trimesh's exporter would (x y z nx ny nz per vertex, uchar-counted int32 face lists)."""
+
+    def __init__(self, vertices, faces, vertex_normals):
+        self.vertices = np.asarray(vertices, dtype=np.float32)
+        self.faces = np.asarray(faces, dtype=np.int32)
+        self.vertex_normals = np.asarray(vertex_normals, dtype=np.float32)
+
+    def export(self, path):
+        nv, nf = self.vertices.shape[0], self.faces.shape[0]
+        header = ("ply\nformat binary_little_endian 1.0\nelement vertex %d\nproperty float x\nproperty float y\n"
+                  "property float z\nproperty float nx\nproperty float ny\nproperty float nz\nelement face %d\n"
+                  "property list uchar int vertex_indices\nend_header\n" % (nv, nf))
+        vert = np.empty(nv, dtype=[("p", "<f4", 3), ("n", "<f4", 3)])
+        vert["p"], vert["n"] = self.vertices, self.vertex_normals
+        face = np.empty(nf, dtype=[("k", "u1"), ("i", "<i4", 3)])
+        face["k"], face["i"] = 3, self.faces
+        with open(path, "wb") as f:
+            f.write(header.encode("ascii"))
+            f.write(vert.tobytes())
+            f.write(face.tobytes())
+        return path
+
+
+def tsdf2mesh(voxel_size, origin, tsdf_vol):
+    """neucon_utils.py:176-180 (`SaveScene.tsdf2mesh`): marching cubes at level 0, vertices to world coordinates."""
+    verts, faces, norms, _ = marching_cubes(tsdf_vol, level=0)
+    verts = verts * np.float32(voxel_size) + np.asarray(origin, dtype=np.float32)  # voxel grid coordinates to world coordinates
+    return TriMesh(verts, faces, norms)
+
+
+def save_scene_eval(save_dir, scene_name, voxel_size, origin, tsdf_volume):
+    """neucon_utils.py:225-244 (`SaveScene.save_scene_eval` for one scene): `<save_dir>/<scene>.npz` with origin / voxel_size /
+    tsdf and `<save_dir>/<scene>.ply`; returns the mesh, or None when the volume holds no surface (all ones)."""
+    import os
+    tsdf_volume = tsdf_volume.detach().cpu().numpy() if torch.is_tensor(tsdf_volume) else np.asarray(tsdf_volume)
+    origin = origin.detach().cpu().numpy() if torch.is_tensor(origin) else np.asarray(origin)
+    if (tsdf_volume == 1).all():
+        return None
+    mesh = tsdf2mesh(voxel_size, origin, tsdf_volume)
+    os.makedirs(save_dir, exist_ok=True)
+    np.savez_compressed(os.path.join(save_dir, "%s.npz" % scene_name), origin=origin, voxel_size=voxel_size, tsdf=tsdf_volume)
+    mesh.export(os.path.join(save_dir, "%s.ply" % scene_name))
+    return mesh

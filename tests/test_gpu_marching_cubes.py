@@ -82,3 +82,21 @@ def test_tsdf_volume_get_mesh_and_point_cloud():
         datagen.meshwrite(path, verts, faces, norms, colors)
         head = open(path).read(400)
         assert "element vertex %d" % verts.shape[0] in head and "element face %d" % faces.shape[0] in head
+
+
+def test_tsdf2mesh_and_save_scene_eval(tmp_path):
+    """neucon_utils.py:176-180, 225-244: scene volume -> world-space mesh -> .npz + .ply on disk."""
+    from deep3dmap_b200 import mesh
+    vol, _ = _volumes()["sphere"]
+    origin = np.array([1.0, -2.0, 0.5], np.float32)
+    m = mesh.save_scene_eval(str(tmp_path), "scene0000_00", 0.04, torch.from_numpy(origin), torch.from_numpy(vol).cuda())
+    ov, of, on = omc.marching_cubes(vol, 0.0)
+    np.testing.assert_array_equal(m.faces, of)
+    np.testing.assert_allclose(m.vertices, ov * np.float32(0.04) + origin, rtol=0, atol=1e-6)
+    data = np.load(str(tmp_path / "scene0000_00.npz"))
+    assert sorted(data.files) == ["origin", "tsdf", "voxel_size"] and np.array_equal(data["tsdf"], vol)
+    raw = open(str(tmp_path / "scene0000_00.ply"), "rb").read()
+    head, body = raw.split(b"end_header\n", 1)
+    assert b"element vertex %d" % ov.shape[0] in head and b"element face %d" % of.shape[0] in head
+    assert len(body) == ov.shape[0] * 24 + of.shape[0] * 13
+    assert mesh.save_scene_eval(str(tmp_path), "empty", 0.04, origin, np.ones((4, 4, 4), np.float32)) is None
