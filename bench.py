@@ -45,6 +45,8 @@ def ncu_traffic(kernel, level):
     p = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     try:
         t = json.load(open(p))
+        if kernel == "__step__":   # every launch of the captured step
+            return int(sum(sum(v) for v in t["kernels"].values())), t["source"]
         return t["kernels"][kernel][level], t["source"]
     except Exception:
         return None, None
@@ -692,6 +694,7 @@ def run_ours(args, rank, world, local_rank):
     cb = levels[li]["coords"].dtype.itemsize * 4
     touched = kernel_touched_bytes(dom, N_dom, S_dom, V, B, C, H, W, cb)
     traffic, traffic_src = ncu_traffic(dom, li)
+    step_traffic, _ = ncu_traffic("__step__", 0)
     a_path = sum(sum(algorithmic_bytes(l, s_)) for l, s_ in zip(levels, S_levels))
     path_gbs = a_path / (ms_step * 1e-3) / 1e9
     FWD_K = ("relayout_transpose", "bp_prep", "zero_words", "bp_fwd", "bp_fwd_stats", "bp_fwd_normalise", "bp_fwd_finish")
@@ -741,7 +744,8 @@ def run_ours(args, rank, world, local_rank):
                      "achieved": path_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": path_gbs / peak_gbs,
                      "frac_of_nominal_8TBs": path_gbs / 8000.0, "peak_source": peak_src,
                      "algorithmic_bytes_per_step": int(a_path), "ms_per_step": ms_step,
-                     "traffic": traffic, "traffic_source": traffic_src,
+                     "traffic": step_traffic, "traffic_source": traffic_src,
+                     "traffic_what": "DRAM bytes (read + write) of every launch of one L2-flushed step, summed",
                      "formula": "SURVEY 8(d): sum over levels of A_fwd + A_bwd, divided by the timed step (graph replay, L2 "
                                 "flushed); 16*C*S counts the 4 corner texels of every valid sample, which the L2-resident maps "
                                 "serve -- DRAM traffic is far lower (see dominant_kernel.traffic)",
@@ -875,7 +879,8 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     coords_all = synth.large_scene_coords(dtype=np.int32)
     N = coords_all.shape[0]
     # block-cyclic ranges: the camera lattice covers the scene unevenly, contiguous ranges would be unbalanced
-    mine = shard.voxel_blocks(N, rank, world)
+    block = int(os.environ.get("D3M_BENCH_BLOCK", "4096"))
+    mine = shard.voxel_blocks(N, rank, world, block=block)
     coords = torch.from_numpy(np.ascontiguousarray(coords_all[mine.numpy()])).to(dev)
     n_local = int(mine.numel())
     R, c = synth.large_scene_cameras(V)
@@ -892,7 +897,7 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
         # gradient of ITS V / world views (what a view-parallel 2D backbone consumes) + all-gather of the view counts
         # (peer stores of every rank's rows at their positions in the scene's voxel order: no gather collective)
         vol, cnt, grad_fn, full = shard.back_project_voxel_sharded_view_owner(coords, origin, synth.VOXEL_SIZE, feats, KR,
-                                                                              count_rows=(N, 0, 4096))
+                                                                              count_rows=(N, 0, block))
         g_own, vr = grad_fn(go)
         return full, cnt, g_own, vr
 
@@ -947,7 +952,7 @@ def bench_large_scene(torch, dist, dev, flush_buf, rank, world):
     _lib.profile_begin()
     step()
     kern = {k: round(v["ms"], 3) for k, v in sorted(_lib.profile_end().items())}
-    res = {"kernel_ms_rank0": kern, "index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": n_local, "partition": "block-cyclic voxel ranges (4096 voxels per block)",
+    res = {"kernel_ms_rank0": kern, "index_space": "1024^3 @ 4 cm", "voxels": int(N), "views": V, "level": lv, "voxels_per_rank": n_local, "partition": "block-cyclic voxel ranges (%d voxels per block)" % block,
            "samples_per_step": int(N) * V, "valid_samples": int(S[0].item()), "ms_per_step": ms,
            "samples_per_s": N * V / (ms * 1e-3), "scaling": "strong", "parity": parity,
            "collectives": "all_reduce(3 fp64 per fragment) + grad_feats %.0f MB by %s + view counts (%d B/voxel) all-gathered as "

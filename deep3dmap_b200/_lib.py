@@ -15,7 +15,7 @@ SYMBOLS = (
     "d3m_kernel_launches", "d3m_profile_begin", "d3m_profile_end",
     "d3m_feats_nchw_to_nhwc", "d3m_feats_nhwc_to_nchw",
     "d3m_back_project_fwd_workspace", "d3m_back_project_cell_hist_elems", "d3m_back_project_fwd",
-    "d3m_back_project_fwd_partial", "d3m_back_project_fwd_finish",
+    "d3m_back_project_fwd_partial", "d3m_back_project_fwd_finish", "d3m_back_project_fwd_partial_x",
     "d3m_back_project_bwd_workspace", "d3m_back_project_bwd",
     "d3m_p2p_alloc", "d3m_p2p_open", "d3m_p2p_close", "d3m_p2p_free", "d3m_back_project_bwd_exchange", "d3m_grad_slots_sum",
     "d3m_p2p_scatter_rows", "d3m_p2p_sync_mailbox_bytes", "d3m_p2p_sync",
@@ -42,6 +42,12 @@ _lib = None
 
 class D3MError(RuntimeError):
     pass
+
+
+class CountExchange(ctypes.Structure):
+    """d3m_count_exchange of include/d3m.h"""
+    _fields_ = [("peer_count_host", ctypes.POINTER(ctypes.c_void_p)), ("world", ctypes.c_int), ("rank", ctypes.c_int),
+                ("begin", ctypes.c_int64), ("block", ctypes.c_int64)]
 
 
 def lib():
@@ -74,6 +80,9 @@ def lib():
     L.d3m_back_project_fwd.restype = i32
     L.d3m_back_project_fwd_partial.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd_partial.restype = i32
+    L.d3m_back_project_fwd_partial_x.argtypes = [vp, i32, i64, vp, i32, f32, vp, i32, vp, i32, i32, i32, i32, vp, vp, vp, vp, vp,
+                                                 vp, sz, vp, vp]
+    L.d3m_back_project_fwd_partial_x.restype = i32
     L.d3m_back_project_fwd_finish.argtypes = [i64, i32, i32, vp, vp, vp, sz, vp]
     L.d3m_back_project_fwd_finish.restype = i32
     L.d3m_back_project_bwd_workspace.argtypes = [i64, i32, i32, i32, i32, i32]

@@ -20,6 +20,7 @@
 namespace d3m {
 
 constexpr int kFwdWarps = 4;          // warps per CTA (each fully independent)
+constexpr int kMaxCountPeers = 16;
 constexpr int kMaxViewChunk = 16;     // views whose records are resident in smem at once
 constexpr unsigned kFull = 0xffffffffu;
 constexpr int kFlagX1 = 1 << 30;      // x0+1 < W
@@ -48,6 +49,12 @@ struct FwdParams {
   float* stats;           // (B, 2): mean, sd
   double* sums;           // (B, 3) or NULL (voxel-range sharding: handed to the caller instead of finalising)
   int finalize;
+  // voxel-range sharding: the view count of every voxel also goes, from this kernel, into every rank's full-scene count
+  // buffer at the voxel's global position (peer memory over NVLink) -- the all-gather the next coarse-to-fine level
+  // needs, without a collective and without a pass of its own
+  int xw, xr;             // world size (0 = off), this rank
+  long long xbegin, xblock;   // global row = xbegin + n (contiguous range, xblock == 0) or the block-cyclic map
+  float* xcount[kMaxCountPeers];
   int tv;
   int vchunk;
   int64_t num_tiles;
@@ -293,6 +300,10 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
         p.count[n] = (float)cnt;
         p.zbar[n] = zb;
         p.bidx[n] = b;
+        if (p.xw) {
+          const long long gidx = p.xblock > 0 ? ((n / p.xblock) * p.xw + p.xr) * p.xblock + n % p.xblock : p.xbegin + n;
+          for (int r = 0; r < p.xw; ++r) p.xcount[r][gidx] = (float)cnt;
+        }
       }
     }
     const int rows = (int)min((int64_t)p.tv, p.N - n0);
@@ -421,6 +432,10 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 6) bp_fwd8_kernel(const FwdPar
         p.count[n] = (float)cnt;
         p.zbar[n] = zb;
         p.bidx[n] = b;
+        if (p.xw) {
+          const long long gidx = p.xblock > 0 ? ((n / p.xblock) * p.xw + p.xr) * p.xblock + n % p.xblock : p.xbegin + n;
+          for (int r = 0; r < p.xw; ++r) p.xcount[r][gidx] = (float)cnt;
+        }
       }
     }
     const int rows = (int)min((int64_t)p.tv, p.N - n0);
@@ -519,6 +534,10 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const Fw
         p.count[n] = (float)cnt;
         p.zbar[n] = zb;
         p.bidx[n] = b;
+        if (p.xw) {
+          const long long gidx = p.xblock > 0 ? ((n / p.xblock) * p.xw + p.xr) * p.xblock + n % p.xblock : p.xbegin + n;
+          for (int r = 0; r < p.xw; ++r) p.xcount[r][gidx] = (float)cnt;
+        }
       }
     }
     const int rows = (int)min((int64_t)p.tv, p.N - n0);
@@ -1039,7 +1058,14 @@ static int fwd_finish_launch(int64_t N, int C, const FwdWs& w, unsigned char* ws
 static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float* origin, int B, float voxel_size,
                     const float* feats, int feats_layout, float* feats_nhwc_scratch, int V, int C, int H, int W,
                     const float* KRcam, float* out, float* count, int* cell_hist, void* workspace, size_t workspace_bytes,
-                    double* depth_sums, cudaStream_t stream) {
+                    double* depth_sums, cudaStream_t stream, const d3m_count_exchange* cx = nullptr) {
+  if (cx) {
+    D3M_REQUIRE(cx->peer_count_host && cx->world >= 1 && cx->world <= kMaxCountPeers && cx->rank >= 0 && cx->rank < cx->world &&
+                    cx->begin >= 0 && cx->block >= 0,
+                D3M_ERR_ARG, "back_project: bad count exchange (at most %d ranks)", kMaxCountPeers);
+    for (int r = 0; r < cx->world; ++r)
+      D3M_REQUIRE(cx->peer_count_host[r], D3M_ERR_ARG, "back_project: count buffer of rank %d is NULL", r);
+  }
   int rc = fwd_check(coords, coords_kind, N, origin, B, feats, feats_layout, feats_nhwc_scratch, V, C, H, W, KRcam, out,
                      count, workspace, workspace_bytes);
   if (rc != D3M_OK) return rc;
@@ -1088,6 +1114,10 @@ static int fwd_impl(const void* coords, int coords_kind, int64_t N, const float*
   p.stats = reinterpret_cast<float*>(ws + w.stats);
   p.sums = depth_sums;
   p.finalize = depth_sums ? 0 : 1;
+  if (cx) {
+    p.xw = cx->world; p.xr = cx->rank; p.xbegin = cx->begin; p.xblock = cx->block;
+    for (int r = 0; r < cx->world; ++r) p.xcount[r] = static_cast<float*>(cx->peer_count_host[r]);
+  }
   int fwd_grid = 0, fused = 0;
   if (coords_kind == D3M_COORDS_F32) rc = launch_fwd<D3M_COORDS_F32>(p, stream, &fwd_grid, &fused);
   else if (coords_kind == D3M_COORDS_I64) rc = launch_fwd<D3M_COORDS_I64>(p, stream, &fwd_grid, &fused);
@@ -1146,3 +1176,15 @@ extern "C" int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double
   D3M_CUDA_CHECK(cudaGetLastError());
   return fwd_finish_launch(N, C, w, ws, out, nullptr, nullptr, true, 0, nullptr, stream);
 }
+
+extern "C" int d3m_back_project_fwd_partial_x(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                              float voxel_size, const float* feats, int feats_layout,
+                                              float* feats_nhwc_scratch, int V, int C, int H, int W, const float* KRcam,
+                                              float* out, float* count, int* cell_hist, double* depth_sums,
+                                              void* workspace, size_t workspace_bytes, const d3m_count_exchange* cx,
+                                              void* stream_) {
+  D3M_REQUIRE(depth_sums, D3M_ERR_ARG, "back_project_fwd_partial_x: NULL depth_sums");
+  return fwd_impl(coords, coords_kind, N, origin, B, voxel_size, feats, feats_layout, feats_nhwc_scratch, V, C, H, W,
+                  KRcam, out, count, cell_hist, workspace, workspace_bytes, depth_sums, static_cast<cudaStream_t>(stream_), cx);
+}
+

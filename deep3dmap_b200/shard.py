@@ -120,8 +120,10 @@ class _CudaLocalOps:
     """The per-rank kernels (libd3m.so).  Tests substitute an object with the same three methods."""
 
     @staticmethod
-    def forward_partial(coords, origin, voxel_size, feats, KRcam, want_hist=False):
-        """-> (out (n,C+1) with RAW mean depth in the last column, count (n,), depth_sums (B,3) float64, state)"""
+    def forward_partial(coords, origin, voxel_size, feats, KRcam, want_hist=False, count_exchange=None):
+        """-> (out (n,C+1) with RAW mean depth in the last column, count (n,), depth_sums (B,3) float64, state).
+        `count_exchange`: a `_lib.CountExchange` -- the gather kernel then also stores every count into every rank's
+        full-scene buffer (the fused all-gather of `RowsExchange`)."""
         L = _lib.lib()
         if not feats.is_cuda:
             raise _lib.D3MError("back_project_voxel_sharded: feats must live on a CUDA device (no CPU fallback)")
@@ -140,12 +142,21 @@ class _CudaLocalOps:
             hist = voxel._new_cell_hist(N, B, V, H, W, dev)
         ws, ws_bytes = voxel._workspace("f", (max(N, 1), B, V, C), dev)
         if N > 0:
+            import ctypes
             with voxel._on_device(dev):
-                rc = L.d3m_back_project_fwd_partial(coords.data_ptr(), voxel._COORD_KIND[coords.dtype], N,
-                                                    origin.data_ptr(), B, float(voxel_size), store.data_ptr(), layout,
-                                                    voxel._ptr(scratch), V, C, H, W,
-                                                    KRcam.data_ptr(), out.data_ptr(), count.data_ptr(), voxel._ptr(hist),
-                                                    sums.data_ptr(), ws.data_ptr(), ws_bytes, voxel._stream(dev))
+                if count_exchange is None:
+                    rc = L.d3m_back_project_fwd_partial(coords.data_ptr(), voxel._COORD_KIND[coords.dtype], N,
+                                                        origin.data_ptr(), B, float(voxel_size), store.data_ptr(), layout,
+                                                        voxel._ptr(scratch), V, C, H, W,
+                                                        KRcam.data_ptr(), out.data_ptr(), count.data_ptr(), voxel._ptr(hist),
+                                                        sums.data_ptr(), ws.data_ptr(), ws_bytes, voxel._stream(dev))
+                else:
+                    rc = L.d3m_back_project_fwd_partial_x(coords.data_ptr(), voxel._COORD_KIND[coords.dtype], N,
+                                                          origin.data_ptr(), B, float(voxel_size), store.data_ptr(), layout,
+                                                          voxel._ptr(scratch), V, C, H, W,
+                                                          KRcam.data_ptr(), out.data_ptr(), count.data_ptr(),
+                                                          voxel._ptr(hist), sums.data_ptr(), ws.data_ptr(), ws_bytes,
+                                                          ctypes.byref(count_exchange), voxel._stream(dev))
             _lib.check(rc, "d3m_back_project_fwd_partial")
         return out, count, sums, (ws, ws_bytes, (V, B, H, W, C), coords, origin, KRcam, hist)
 
@@ -348,14 +359,23 @@ class RowsExchange:
         self.n_total, self.width, self.device, self.group = int(n_total), int(width), device, group
         self.rank, self.world = _world(group)
         nbytes = max(16, 4 * self.n_total * self.width)
-        self._own, self._tables, self._views = [], [], []
+        import ctypes
+        self._own, self._tables, self._views, self.host_tables = [], [], [], []
         for _ in range(2):
             own, ptrs = _p2p_buffers(nbytes, device, group)
             self._own.append(own)
+            self.host_tables.append((ctypes.c_void_p * self.world)(*ptrs))
             self._tables.append(torch.tensor(ptrs, dtype=torch.int64, device=device))   # device-side pointer table
             shape = (self.n_total, self.width) if self.width > 1 else (self.n_total,)
             self._views.append(torch.as_tensor(_DevView(own, shape, "<f4", self), device=device))
         self._turn = 0
+
+    def next_buffer(self):
+        """-> (k, this rank's full buffer k): for producers that write the peers' buffers themselves (the forward gather
+        kernel through `_lib.CountExchange(self.host_tables[k], ...)`)."""
+        k = self._turn
+        self._turn ^= 1
+        return k, self._views[k]
 
     def scatter(self, local, begin=0, block=0):
         """Write this rank's rows into every rank's buffer; returns this rank's full buffer (complete after the next
@@ -382,15 +402,17 @@ def back_project_voxel_sharded_view_owner(coords_local, origin, voxel_size, feat
     coarse-to-fine level needs, neucon_network.py:132) as peer stores at the rows' global positions -- `begin` for a
     contiguous `voxel_range`, `block` for `voxel_blocks` -- and return them as a 4th value, in the scene's voxel order."""
     ops = _CudaLocalOps
-    out, count, sums, state = ops.forward_partial(coords_local, origin, voxel_size, feats.detach(), KRcam, want_hist=True)
     rank, world = _world(group)
-    full_count = None
-    if count_rows is not None:
+    cx, full_count = None, None
+    if count_rows is not None and world > 1 and feats.is_cuda:
         n_total, begin, block = count_rows
-        if world > 1:
-            full_count = RowsExchange.get(n_total, 1, out.device, group).scatter(count, begin=begin, block=block)
-        else:
-            full_count = count
+        rex = RowsExchange.get(n_total, 1, feats.device, group)
+        k, full_count = rex.next_buffer()
+        cx = _lib.CountExchange(rex.host_tables[k], world, rank, int(begin), int(block))
+    out, count, sums, state = ops.forward_partial(coords_local, origin, voxel_size, feats.detach(), KRcam, want_hist=True,
+                                                  count_exchange=cx)
+    if count_rows is not None and full_count is None:
+        full_count = count
     if world > 1:
         # 3 fp64 scalars per fragment -- and the barrier after which every rank's count rows have landed
         PeerSync.get(out.device, group).all_reduce_(sums)

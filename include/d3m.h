@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define D3M_VERSION 110
+#define D3M_VERSION 111
 
 enum {
   D3M_OK = 0,
@@ -117,6 +117,20 @@ int d3m_back_project_fwd_partial(const void* coords, int coords_kind, int64_t N,
                                  void* stream);
 int d3m_back_project_fwd_finish(int64_t N, int B, int C, const double* depth_sums, float* out, void* workspace,
                                 size_t workspace_bytes, void* stream);
+/* _partial with the all-gather of the view counts fused into the gather kernel: every voxel's count is also stored into
+ * every rank's full-scene count buffer (peer_count_host: HOST array of `world` device pointers, IPC-mapped, float32) at the
+ * voxel's global row -- begin + n for a contiguous range (block == 0), ((n / block) * world + rank) * block + n % block for
+ * block-cyclic ranges.  Complete everywhere after the caller's next sync across the ranks (d3m_p2p_sync). */
+typedef struct {
+  void* const* peer_count_host;
+  int world, rank;
+  int64_t begin, block;
+} d3m_count_exchange;
+int d3m_back_project_fwd_partial_x(const void* coords, int coords_kind, int64_t N, const float* origin, int B,
+                                   float voxel_size, const float* feats, int feats_layout, float* feats_nhwc_scratch,
+                                   int V, int C, int H, int W, const float* KRcam, float* out, float* count,
+                                   int* cell_hist, double* depth_sums, void* workspace, size_t workspace_bytes,
+                                   const d3m_count_exchange* cx, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * back_project backward w.r.t. feats  (replaces autograd through back_project.py:55-73:

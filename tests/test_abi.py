@@ -31,7 +31,7 @@ def test_exports_every_declared_symbol():
 
 def test_version_and_workspace_queries():
     L = _lib.lib()
-    assert L.d3m_version() == 110
+    assert L.d3m_version() == 111
     assert L.d3m_device_count() >= 0
     assert L.d3m_back_project_fwd_workspace(13824, 1, 9, 80) > 13824 * 8
     # backward: pre-divided rows (N*C*4) + 16-byte entries for every voxel-view pair + cell tables

@@ -64,8 +64,9 @@ def full(rep, out):
             w.writerow([r[c].split("(")[0].replace("void ", "") if c == cols[0] else r[c] for c in cols])
 
 
-LIB_NAMES = {"bp_fwd_kernel": "bp_fwd", "bp_stats_kernel": "bp_fwd_stats", "bp_normalise_kernel": "bp_fwd_normalise",
-             "bp_scan_ghat_kernel": "bp_bwd_scan_ghat", "bp_bwd_order_kernel": "bp_bwd_order",
+LIB_NAMES = {"bp_fwd_kernel": "bp_fwd", "bp_fwd8_kernel": "bp_fwd", "bp_stats_kernel": "bp_fwd_stats",
+             "bp_fwd_finish_kernel": "bp_fwd_finish", "bp_prep_kernel": "bp_prep", "bp_prep4_kernel": "bp_prep",
+             "bp_bwd_fill_ghat_kernel": "bp_bwd_fill_ghat", "bp_bwd_order_kernel": "bp_bwd_order",
              "bp_bwd_gather_tile_kernel": "bp_bwd_gather", "transpose_maps_kernel": "relayout_transpose"}
 
 
