@@ -442,6 +442,34 @@ def run_ours(args, rank, world, local_rank):
             outs.append((vol, cnt))
         return outs
 
+    # The three level passes of the step are independent of each other (in training the 3D network sits between them):
+    # issued on one stream per level, largest level first, the small launches of the coarse levels (13824 and 27192
+    # voxels: a fraction of one wave) run under the fine level's kernels instead of in front of them.
+    lvl_streams = [torch.cuda.Stream(device=dev) for _ in dl]
+
+    def step_level_streams():
+        cur = torch.cuda.current_stream()
+        outs = []
+        for d, st in sorted(zip(dl, lvl_streams), key=lambda x: -x[0]["coords"].shape[0]):
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                d["feats"].grad = None
+                vol, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+                vol.backward(d["go"])
+                outs.append((vol, cnt))
+        for st in lvl_streams:
+            cur.wait_stream(st)
+        return outs
+
+    def step_one_backward():
+        # the three forwards, then ONE autograd pass over the three outputs -- how a training loop reaches them (one
+        # loss.backward() for the whole network): the engine's start-up and thread hand-off are paid once, not per level
+        for d in dl:
+            d["feats"].grad = None
+        vols = [back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])[0] for d in dl]
+        torch.autograd.backward(vols, [d["go"] for d in dl])
+        return vols
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -500,24 +528,43 @@ def run_ours(args, rank, world, local_rank):
     launches0 = _lib.kernel_launches()
     ms_eager = timed(step_resident)
     launches = _lib.kernel_launches() - launches0
-    graph, graph_err = None, None
-    if not args.no_graph:
+    for _ in range(3):
+        step_one_backward()
+    ms_eager_1b = timed(step_one_backward)
+    def capture(fn):
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                step_resident()
+                fn()
             torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                step_resident()
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                fn()
             for _ in range(3):
-                graph.replay()
+                g.replay()
             torch.cuda.synchronize()
+            return g, None
         except Exception as err:  # capture is an optimisation, never a requirement
-            graph, graph_err = None, repr(err)[:200]
             torch.cuda.synchronize()
-    ms_graph = timed(graph.replay) if graph is not None else None
+            return None, repr(err)[:200]
+
+    graph, graph_err, graph_lv, graph_lv_err = None, None, None, None
+    ms_eager_lv = None
+    if not args.no_graph:
+        graph, graph_err = capture(step_resident)
+        if os.environ.get("D3M_BENCH_LEVEL_STREAMS", "1") != "0":
+            for _ in range(3):
+                step_level_streams()
+            ms_eager_lv = timed(step_level_streams)
+            graph_lv, graph_lv_err = capture(step_level_streams)
+    ms_graph_serial = timed(graph.replay) if graph is not None else None
+    ms_graph_lv = timed(graph_lv.replay) if graph_lv is not None else None
+    ms_graph = ms_graph_serial
+    step_mode = "cuda_graph_replay" if ms_graph is not None else "eager"
+    if ms_graph_lv is not None and (ms_graph is None or ms_graph_lv < ms_graph):
+        ms_graph, step_mode = ms_graph_lv, "cuda_graph_replay, one captured branch per level (3 concurrent streams)"
     ms_step = ms_graph if ms_graph is not None else ms_eager
     # host-side issue cost of one eager step (python + autograd + ctypes + launches), GPU idle at start
     torch.cuda.synchronize()
@@ -736,10 +783,13 @@ def run_ours(args, rank, world, local_rank):
                 "levels issued before the backward phase, so that H2D, kernels and D2H overlap (PCIe-bound: the step "
                 "moves 51 MB in and 47 MB out)"},
         "gpu_launches": int(launches), "host_issue_ms_per_step": host_ms,
-        "step_mode": "cuda_graph_replay" if ms_graph is not None else "eager", "ms_per_step_eager": ms_eager,
-        "kernel_chaining": ("programmatic dependent launch (griddepcontrol)" if os.environ.get("D3M_PDL", "1") != "0"
-                            else "plain stream serialisation (D3M_PDL=0)"),
-        "ms_per_step_graph": ms_graph, "graph_error": graph_err,
+        "step_mode": step_mode, "ms_per_step_eager": ms_eager, "ms_per_step_eager_level_streams": ms_eager_lv,
+        "ms_per_step_eager_single_backward": ms_eager_1b,
+        "kernel_chaining": {"0": "plain stream serialisation (D3M_PDL=0)", "1": "programmatic dependent launch on every "
+                            "launch (D3M_PDL=1)"}.get(os.environ.get("D3M_PDL", "auto"), "programmatic dependent launch for "
+                            "small eager calls, plain stream order under graph capture and for large launches (D3M_PDL=auto)"),
+        "ms_per_step_graph": ms_graph, "ms_per_step_graph_serial": ms_graph_serial,
+        "ms_per_step_graph_level_streams": ms_graph_lv, "graph_error": graph_err or graph_lv_err,
         "roofline": {"bound": "hbm", "kernel": "whole step: back_project fwd+bwd x 3 levels (every kernel of the path)",
                      "achieved": path_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": path_gbs / peak_gbs,
                      "frac_of_nominal_8TBs": path_gbs / 8000.0, "peak_source": peak_src,

@@ -55,7 +55,8 @@ struct FwdParams {
   int xw, xr;             // world size (0 = off), this rank
   long long xbegin, xblock;   // global row = xbegin + n (contiguous range, xblock == 0) or the block-cyclic map
   float* xcount[kMaxCountPeers];
-  int tv;
+  int tv, tv_log2;
+  unsigned jpat;  // bit k*tv set for every k: the lanes of voxel 0 of a tile (see push_records)
   int vchunk;
   int64_t num_tiles;
   int per_warp_bytes;
@@ -75,31 +76,71 @@ __device__ __forceinline__ void bulk_store_tile(float* gdst, const float* ssrc, 
   __syncwarp();
 }
 
-// phase 1 for one chunk of views; returns the number of records pushed by this lane
+// phase 1 for one chunk of views: the 32 lanes of the warp are (view slot, voxel) pairs -- lane = slot * tv + j holds
+// voxel j of the tile and projects views vb + slot of each pass of 32 / tv views, so a 4-voxel tile of the coarse level
+// walks its 9 views in 2 dependent projections instead of 9 (a 32-voxel tile: one view per pass, as before).  A valid
+// sample's record slot is the voxel's count so far plus its rank among the valid lanes of the same voxel (ballot; the
+// lanes of a voxel are in view order), so the records of a voxel stay in ascending view order and the depth sum -- formed
+// by the voxel's first lane from the recorded depths, in that order -- keeps the reference's summation order.
+// Returns the number of records of voxel j (the same in every lane of the voxel).
 template <int KIND>
 __device__ __forceinline__ int push_records(const FwdParams& p, int b, int64_t n, float gx, float gy, float gz, int v0,
-                                            int v1, int lane, int* rec_off, float* rec_fx, float* rec_fy, float& zsum) {
+                                            int v1, int lane, int* rec_off, float* rec_fx, float* rec_fy, float* rec_z,
+                                            float& zsum) {
+  const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
   int ccnt = 0;
-  if (b >= 0) {
-    const float wm1 = (float)(p.W - 1), hm1 = (float)(p.H - 1);
-    for (int v = v0; v < v1; ++v) {
-      float4 r0, r1, r2;
-      load_krcam(p.KR, v, p.B, b, r0, r1, r2);
-      const Sample s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
-      if (s.valid) {
-        int off = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
-        if (p.cell_hist)  // integer RED: order-independent
-          atomicAdd(p.cell_hist + (((int64_t)off << p.nb_log2) + ((int)n & ((1 << p.nb_log2) - 1))), 1);
-        if (s.x0 + 1 < p.W) off |= kFlagX1;
-        if (s.y0 + 1 < p.H) off |= kFlagY1;
-        rec_off[ccnt * 32 + lane] = off;
-        rec_fx[ccnt * 32 + lane] = s.fx;
-        rec_fy[ccnt * 32 + lane] = s.fy;
-        ++ccnt;
-        zsum = __fadd_rn(zsum, s.z);
+  if (p.tv == 32) {
+    // full tiles: one lane per voxel, views in sequence (the ballot / recorded-depth bookkeeping below costs the fine
+    // level 3 us per launch and buys nothing when every lane already holds a voxel)
+    if (b >= 0) {
+      for (int v = v0; v < v1; ++v) {
+        float4 r0, r1, r2;
+        load_krcam(p.KR, v, p.B, b, r0, r1, r2);
+        const Sample s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
+        if (s.valid) {
+          int off = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
+          if (p.cell_hist) atomicAdd(p.cell_hist + (((int64_t)off << p.nb_log2) + ((int)n & ((1 << p.nb_log2) - 1))), 1);
+          if (s.x0 + 1 < p.W) off |= kFlagX1;
+          if (s.y0 + 1 < p.H) off |= kFlagY1;
+          rec_off[ccnt * 32 + lane] = off;
+          rec_fx[ccnt * 32 + lane] = s.fx;
+          rec_fy[ccnt * 32 + lane] = s.fy;
+          ++ccnt;
+          zsum = __fadd_rn(zsum, s.z);
+        }
       }
     }
+    return ccnt;
   }
+  const int j = lane & (p.tv - 1), slot = lane >> p.tv_log2, vpp = 32 >> p.tv_log2;
+  const unsigned jmask = p.jpat << j, below = jmask & ((1u << lane) - 1u);
+  for (int vb = v0; vb < v1; vb += vpp) {
+    const int v = vb + slot;
+    Sample s;
+    s.valid = false;
+    if (b >= 0 && v < v1) {
+      float4 r0, r1, r2;
+      load_krcam(p.KR, v, p.B, b, r0, r1, r2);
+      s = project(gx, gy, gz, r0, r1, r2, wm1, hm1);
+    }
+    const unsigned bal = __ballot_sync(kFull, s.valid);
+    if (s.valid) {
+      int off = ((v * p.B + b) * p.H + s.y0) * p.W + s.x0;
+      if (p.cell_hist)  // integer RED: order-independent
+        atomicAdd(p.cell_hist + (((int64_t)off << p.nb_log2) + ((int)n & ((1 << p.nb_log2) - 1))), 1);
+      if (s.x0 + 1 < p.W) off |= kFlagX1;
+      if (s.y0 + 1 < p.H) off |= kFlagY1;
+      const int at = (ccnt + __popc(bal & below)) * 32 + j;
+      rec_off[at] = off;
+      rec_fx[at] = s.fx;
+      rec_fy[at] = s.fy;
+      rec_z[at] = s.z;
+    }
+    ccnt += __popc(bal & jmask);
+  }
+  __syncwarp();
+  if (lane < p.tv)
+    for (int k = 0; k < ccnt; ++k) zsum = __fadd_rn(zsum, rec_z[k * 32 + lane]);
   return ccnt;
 }
 
@@ -194,7 +235,8 @@ __device__ __forceinline__ void fold_partials(const double* __restrict__ partial
 }
 
 template <int KIND, int G, int R>
-__global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams p) {
+__global__ void __launch_bounds__(kFwdWarps * 32, 6) bp_fwd_kernel(const FwdParams p) {  // 6 CTAs/SM: <= 80 registers
+
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -206,16 +248,17 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
   int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
   float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
   float* rec_fy = rec_fx + p.vchunk * 32;
+  float* rec_z = rec_fy + p.vchunk * 32;
   const float4* __restrict__ feats4 = reinterpret_cast<const float4*>(p.feats);
 
   for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
        tile += (int64_t)gridDim.x * kFwdWarps) {
     const int64_t n0 = tile * p.tv;
-    const int64_t n = n0 + lane;
+    const int64_t n = n0 + (lane & (p.tv - 1));  // lanes tv.. repeat the tile's voxels (view slots of push_records)
     const bool active = lane < p.tv && n < p.N;
     int b = -1;
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    if (active) {
+    if (n < p.N) {
       float cx, cy, cz;
       b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
       if (b >= 0) {
@@ -228,7 +271,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_kernel(const FwdParams 
     for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
       const int v1 = min(p.V, v0 + p.vchunk);
       const bool first = (v0 == 0), last = (v1 == p.V);
-      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, rec_z, zsum);
       cnt += ccnt;
       __syncwarp();
       for (int r = 0; r * NG < p.tv; ++r) {
@@ -346,15 +389,16 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 6) bp_fwd8_kernel(const FwdPar
   int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
   float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
   float* rec_fy = rec_fx + p.vchunk * 32;
+  float* rec_z = rec_fy + p.vchunk * 32;
 
   for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
        tile += (int64_t)gridDim.x * kFwdWarps) {
     const int64_t n0 = tile * p.tv;
-    const int64_t n = n0 + lane;
+    const int64_t n = n0 + (lane & (p.tv - 1));  // lanes tv.. repeat the tile's voxels (view slots of push_records)
     const bool active = lane < p.tv && n < p.N;
     int b = -1;
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    if (active) {
+    if (n < p.N) {
       float cx, cy, cz;
       b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
       if (b >= 0) {
@@ -367,7 +411,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32, 6) bp_fwd8_kernel(const FwdPar
     for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
       const int v1 = min(p.V, v0 + p.vchunk);
       const bool first = (v0 == 0), last = (v1 == p.V);
-      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, rec_z, zsum);
       cnt += ccnt;
       __syncwarp();
       for (int r = 0; r * NG < p.tv; ++r) {
@@ -465,15 +509,16 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const Fw
   int* rec_off = reinterpret_cast<int*>(wbase + align_up_dev(p.tv * C1 * 4));
   float* rec_fx = reinterpret_cast<float*>(rec_off + p.vchunk * 32);
   float* rec_fy = rec_fx + p.vchunk * 32;
+  float* rec_z = rec_fy + p.vchunk * 32;
 
   for (int64_t tile = (int64_t)blockIdx.x * kFwdWarps + warp; tile < p.num_tiles;
        tile += (int64_t)gridDim.x * kFwdWarps) {
     const int64_t n0 = tile * p.tv;
-    const int64_t n = n0 + lane;
+    const int64_t n = n0 + (lane & (p.tv - 1));  // lanes tv.. repeat the tile's voxels (view slots of push_records)
     const bool active = lane < p.tv && n < p.N;
     int b = -1;
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    if (active) {
+    if (n < p.N) {
       float cx, cy, cz;
       b = load_coord<KIND>(p.coords, n, p.B, cx, cy, cz);
       if (b >= 0) {
@@ -486,7 +531,7 @@ __global__ void __launch_bounds__(kFwdWarps * 32) bp_fwd_generic_kernel(const Fw
     for (int v0 = 0; v0 < p.V; v0 += p.vchunk) {
       const int v1 = min(p.V, v0 + p.vchunk);
       const bool first = (v0 == 0), last = (v1 == p.V);
-      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, zsum);
+      const int ccnt = push_records<KIND>(p, b, n, gx, gy, gz, v0, v1, lane, rec_off, rec_fx, rec_fy, rec_z, zsum);
       cnt += ccnt;
       __syncwarp();
       for (int j = 0; j < p.tv; ++j) {
@@ -926,9 +971,11 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream, int* grid_out, i
   int tv = 32;
   while (tv > tv_floor && (p.N + tv - 1) / tv < (int64_t)sms * warps_per_sm) tv >>= 1;
   p.tv = tv;
+  p.tv_log2 = tv == 32 ? 5 : tv == 16 ? 4 : tv == 8 ? 3 : 2;
+  p.jpat = tv == 32 ? 1u : 0xffffffffu / ((1u << tv) - 1u);
   p.vchunk = p.V < kMaxViewChunk ? p.V : kMaxViewChunk;
   p.num_tiles = (p.N + tv - 1) / tv;
-  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)3 * p.vchunk * 32 * 4, 16);
+  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)4 * p.vchunk * 32 * 4, 16);
   const size_t smem = (size_t)p.per_warp_bytes * kFwdWarps;
   D3M_REQUIRE(smem <= 200 * 1024, D3M_ERR_ARG, "back_project: C=%d needs %zu B shared memory per CTA", p.C, smem);
   D3M_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem));

@@ -7,6 +7,7 @@ the hand-written sm_100a kernels of `libd3m.so` (forward: `csrc/back_project_fwd
 backward w.r.t. `feats`: `csrc/back_project_bwd.cu`).  PyTorch only provides device memory, the
 current stream and the autograd hook.  There is no fallback path: CPU tensors raise.
 """
+import collections
 import os
 
 import torch
@@ -79,6 +80,30 @@ def _memo(key, query):
             _ws_cache.clear()
         n = _ws_cache[key] = query()
     return n
+
+
+_transient_cache = collections.OrderedDict()
+_TRANSIENT_MAX = 24
+
+
+def _transient(nbytes, dev, stream):
+    """Scratch that no kernel outside the current call reads (the channels-last copy of the maps, the backward
+    workspace): successive calls on one stream are ordered by the stream, so they can share one buffer per (device, stream,
+    size) -- an eager fragment-sized step is host-bound and every `torch.empty` is ~3.5 us.  Small LRU; bypassed under CUDA
+    graph capture (a buffer born in a graph's private pool must not leak into eager calls)."""
+    if torch.cuda.is_current_stream_capturing():
+        return torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    key = (dev.index, stream, nbytes)
+    t = _transient_cache.pop(key, None)      # pop + re-insert = move to the young end (autograd calls from its own thread)
+    if t is None:
+        while len(_transient_cache) >= _TRANSIENT_MAX:
+            try:
+                _transient_cache.popitem(last=False)
+            except KeyError:
+                break
+        t = torch.empty((nbytes,), dtype=torch.uint8, device=dev)
+    _transient_cache[key] = t
+    return t
 
 
 def _new_cell_hist(N, B, V, H, W, dev):
@@ -181,10 +206,11 @@ def _forward_raw(coords, origin, voxel_size, feats, KRcam, cell_hist, nchw):
     count = torch.empty((N,), dtype=torch.float32, device=dev)
     buf, ws_bytes = None, 0
     if N > 0:
-        scratch = torch.empty((V, B, H, W, C), dtype=torch.float32, device=dev) if nchw else None
+        stream = _stream(dev)
+        scratch = _transient(4 * V * B * H * W * C, dev, stream) if nchw else None
         # ONE allocation for the call's workspace and, behind it, the binning state handed to backward (an eager
         # fragment-sized step is host-bound: every torch.empty is ~3 us)
-        ws_bytes = _memo(("f", N, B, V, C), lambda: (L.d3m_back_project_fwd_workspace(N, B, V, C) + 255) // 256 * 256)
+        ws_bytes = _memo(("f256", N, B, V, C), lambda: (L.d3m_back_project_fwd_workspace(N, B, V, C) + 255) // 256 * 256)
         hist_elems = _memo(("h", N, B, V, H, W), lambda: L.d3m_back_project_cell_hist_elems(N, B, V, H, W)) if cell_hist else 0
         buf = torch.empty((ws_bytes + 4 * hist_elems,), dtype=torch.uint8, device=dev)
         hist_ptr = buf.data_ptr() + ws_bytes if cell_hist else None
@@ -192,7 +218,7 @@ def _forward_raw(coords, origin, voxel_size, feats, KRcam, cell_hist, nchw):
             rc = L.d3m_back_project_fwd(coords.data_ptr(), _COORD_KIND[coords.dtype], N, origin.data_ptr(), B,
                                         float(voxel_size), feats.data_ptr(), _lib.FEATS_NCHW if nchw else _lib.FEATS_NHWC,
                                         _ptr(scratch), V, C, H, W, KRcam.data_ptr(), out.data_ptr(), count.data_ptr(),
-                                        hist_ptr, buf.data_ptr(), ws_bytes, _stream(dev))
+                                        hist_ptr, buf.data_ptr(), ws_bytes, stream)
         _lib.check(rc, "d3m_back_project_fwd")
     return out, count, buf, ws_bytes
 
@@ -217,12 +243,14 @@ def back_project_backward(coords, origin, voxel_size, feats_shape_nhwc, KRcam, g
         grad = torch.empty(shape, dtype=torch.float32, device=dev)
     if grad.numel() == 0:
         return grad
-    ws, ws_bytes = _workspace("b", (N, B, V, C, H, W), dev)
+    stream = _stream(dev)
+    ws_bytes = _memo(("b", N, B, V, C, H, W), lambda: L.d3m_back_project_bwd_workspace(N, B, V, C, H, W))
+    ws = _transient(ws_bytes, dev, stream)
     with _on_device(dev):
         rc = L.d3m_back_project_bwd(_ptr(coords), _COORD_KIND[coords.dtype], N, _ptr(origin), B, float(voxel_size),
                                     V, C, H, W, _ptr(KRcam), _ptr(grad_out), _ptr(count),
                                     cell_hist if isinstance(cell_hist, int) else _ptr(cell_hist), grad.data_ptr(),
-                                    1 if nchw else 0, ws.data_ptr(), ws_bytes, _stream(dev))
+                                    1 if nchw else 0, ws.data_ptr(), ws_bytes, stream)
     _lib.check(rc, "d3m_back_project_bwd")
     return grad
 

@@ -21,11 +21,26 @@ levels = bench.build_fragment_levels(cnt_fn)
 dl = [dict(coords=t(i["coords"]), origin=t(i["origin"]), vs=i["voxel_size"], feats=t(i["feats"]).requires_grad_(True),
            KR=t(i["KRcam"]), go=t(i["grad_out"])) for i in levels]
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-def step():
+def step_serial():
     for d in dl:
         d["feats"].grad = None
         vol, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
         vol.backward(d["go"])
+streams = [torch.cuda.Stream() for _ in dl]
+def step_streams():      # STEP_STREAMS=1: one stream per level, largest level first (bench.py step_level_streams)
+    cur = torch.cuda.current_stream()
+    for d, st in sorted(zip(dl, streams), key=lambda x: -x[0]["coords"].shape[0]):
+        st.wait_stream(cur)
+        with torch.cuda.stream(st):
+            d["feats"].grad = None
+            vol, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+            vol.backward(d["go"])
+    for st in streams: cur.wait_stream(st)
+def step_one_backward():  # STEP_ONEBWD=1: three forwards, one autograd pass (bench.py step_one_backward)
+    for d in dl: d["feats"].grad = None
+    vols = [back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])[0] for d in dl]
+    torch.autograd.backward(vols, [d["go"] for d in dl])
+step = step_streams if os.environ.get("STEP_STREAMS") == "1" else step_one_backward if os.environ.get("STEP_ONEBWD") == "1" else step_serial
 def timed(fn, reps=30):
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     torch.cuda.synchronize()
