@@ -903,6 +903,17 @@ static int tsdf_launch(d3m_tsdf* h, const float* depth, const float* cimg, int F
   return D3M_OK;
 }
 
+// Frames per prep -> cull -> integrate round of a batched call.  The depth frames are read twice, by the prep kernel
+// (block maxima) and by the integrate kernel; a round whose frames fit in L2 pays DRAM for them once.
+// D3M_TSDF_GROUP=<frames> overrides; 0 = as many as one launch can take.
+static int frames_per_group(int H, int W) {
+  static const int env = getenv("D3M_TSDF_GROUP") ? atoi(getenv("D3M_TSDF_GROUP")) : 0;
+  int g = env > 0 ? env : kMaxFramesPerLaunch;
+  (void)H; (void)W;
+  if (g > kMaxFramesPerLaunch) g = kMaxFramesPerLaunch;
+  return g;
+}
+
 static int ensure_frames(d3m_tsdf* h, int F) {
   if (F <= h->frames_cap) return D3M_OK;
   int cap = h->frames_cap ? h->frames_cap : 16;
@@ -1068,8 +1079,9 @@ extern "C" int d3m_tsdf_integrate_device(d3m_tsdf* h, const float* depth, const 
   DeviceGuard dev_guard(h->device);
   D3M_CUDA_CHECK(dev_guard.error());
   h->last_launches = 0;
-  for (int f0 = 0; f0 < n_frames; f0 += kMaxFramesPerLaunch) {
-    const int F = (n_frames - f0) < kMaxFramesPerLaunch ? (n_frames - f0) : kMaxFramesPerLaunch;
+  const int group = frames_per_group(H, W);
+  for (int f0 = 0; f0 < n_frames; f0 += group) {
+    const int F = (n_frames - f0) < group ? (n_frames - f0) : group;
     const float* d_frames = nullptr;
     int rc = ensure_frames(h, F);
     if (rc != D3M_OK) return rc;

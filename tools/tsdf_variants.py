@@ -20,7 +20,8 @@ v.reset(); torch.cuda.synchronize(); a.record()
 for f in range(F): v.integrate_batch(d[f:f+1],K,P[f:f+1])
 b.record(); torch.cuda.synchronize()
 w=torch.as_tensor(v.device_volumes()[1],device="cuda")
-print("variant", os.environ.get("D3M_TSDF_VARIANT"), "batch300 ms", min(ts), "per-frame us", a.elapsed_time(b)/F*1e3, "checksum", float(w.double().sum()))
+print("variant", os.environ.get("D3M_TSDF_VARIANT"), "group", os.environ.get("D3M_TSDF_GROUP"), "batch300 ms", min(ts), "per-frame us", a.elapsed_time(b)/F*1e3, "checksum", float(w.double().sum()))
 '''
-for var in sys.argv[1:] or ["0", "1", "2", "3"]:
-    subprocess.run([sys.executable, "-c", code], env=dict(os.environ, D3M_TSDF_VARIANT=var))
+for var in sys.argv[1:] or ["0", "1", "2", "3"]:      # "<variant>" or "<variant>:<frames per group>"
+    v, _, g = var.partition(":")
+    subprocess.run([sys.executable, "-c", code], env=dict(os.environ, D3M_TSDF_VARIANT=v, D3M_TSDF_GROUP=g or "0"))
