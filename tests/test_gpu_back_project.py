@@ -89,6 +89,33 @@ def test_many_views_chunked_and_generic_channels():
     check_vs_oracle("V21 C7", inp, vol, cnt, g)
 
 
+@pytest.mark.parametrize("N", [37, 20000, 50000])
+def test_partial_tiles_project_views_in_parallel(N):
+    """Launches below one wave shrink the warp tile to 4 / 8 / 16 voxels and spread the views of a tile over the idle lanes
+    (push_records): 37, 20000 and 50000 voxels select tiles of 4, 8 and 16; V = 21 > 16 adds the view-chunk loop, so a
+    voxel's record slots and its depth sum cross chunk boundaries.  Count, features (bit-exact) and the summation order
+    of the depth channel must not depend on the tile shape."""
+    rng = np.random.default_rng(N)
+    V, B, C, H, W = 21, 2, 24, 30, 40
+    R, c = synth.fragment_cameras(V)
+    K = np.array([[33.0, 0, 19.5], [0, 33.0, 14.5], [0, 0, 1]])
+    KR = np.stack([synth.krcam_from(R, c + np.array([0.0, 0.3 * b, 0.0]), K) for b in range(B)], 1)
+    coords = np.concatenate([rng.integers(0, B, (N, 1)), rng.integers(0, 96, (N, 3))], 1).astype(np.int64)
+    inp = dict(coords=coords, origin=np.zeros((B, 3), np.float32), voxel_size=0.04,
+               feats=rng.standard_normal((V, B, C, H, W), dtype=np.float32), KRcam=KR.astype(np.float32),
+               grad_out=rng.standard_normal((N, C + 1), dtype=np.float32))
+    vol, cnt, g = run_cuda(inp)
+    assert cnt.max() > 16 and (cnt == 0).any()
+    check_vs_oracle("partial tiles N=%d" % N, inp, vol, cnt, g)
+    # the mean depth BEFORE normalisation is a plain fp32 sum in view order: the 32-voxel-tile launch of the same voxels
+    # (repeated until the launch is a full wave) must give the same bits
+    reps = -(-160000 // N)
+    big = dict(inp, coords=np.tile(coords, (reps, 1)), grad_out=np.tile(inp["grad_out"], (reps, 1)))
+    vol_b, cnt_b, _ = run_cuda(big, grad=False)
+    np.testing.assert_array_equal(cnt_b[:N], cnt)
+    np.testing.assert_array_equal(vol_b[:N, :C], vol[:, :C])
+
+
 @pytest.mark.parametrize("C", [8, 12, 16, 20, 32, 64, 96, 128])
 def test_other_channel_counts(C):
     rng = np.random.default_rng(C)
