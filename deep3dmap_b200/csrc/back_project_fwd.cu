@@ -3,9 +3,10 @@
 // Replaces deep3dmap/core/voxel/back_project.py:23-84 of the reference (≈40 aten kernels per fragment).
 //
 // Work decomposition (one warp = one tile of `tv` consecutive voxels, no block-level sync at all):
-//   phase 1  lane <-> voxel: project the voxel into every view in order, keep count / z-sum in registers and
-//            push a 12-byte record {texel offset|corner flags, fx, fy} for every VALID view into the warp's
-//            shared-memory list (compacted, view order preserved).  Invalid samples cost nothing later.
+//   phase 1  lane <-> (voxel, view slot): a full tile gives every lane one voxel, projected into every view in order;
+//            a partial tile (small launches: 16 / 8 / 4 voxels) spreads each voxel's views over 2 / 4 / 8 lanes
+//            (push_records).  Either way a 12-byte record {texel offset|corner flags, fx, fy} for every VALID view goes
+//            into the warp's shared-memory list (compacted, view order preserved).  Invalid samples cost nothing later.
 //   phase 2  lane group (G lanes, each R float4 = 4*G*R channels) <-> voxel: walk the voxel's record list;
 //            per record 4*R 128-bit channels-last texel loads per lane (one texel = C contiguous floats), the
 //            4-corner FMA chain in the aten order nw,ne,sw,se, then a separate add into the view sum.
@@ -235,7 +236,10 @@ __device__ __forceinline__ void fold_partials(const double* __restrict__ partial
 }
 
 template <int KIND, int G, int R>
-__global__ void __launch_bounds__(kFwdWarps * 32, 6) bp_fwd_kernel(const FwdParams p) {  // 6 CTAs/SM: <= 80 registers
+// 7 CTAs per SM (<= 72 registers) for one float4 per lane, 6 (<= 80) for more: without the bound the partial-tile
+// bookkeeping of push_records pushed the level-0 shape to 88 registers (a second wave), with a flat 6 the level-2 shape grew
+// from 72 to 80 and lost its seventh CTA (dense forward 187 -> 194 us).
+__global__ void __launch_bounds__(kFwdWarps * 32, R == 1 ? 7 : 6) bp_fwd_kernel(const FwdParams p) {
 
   pdl_enter();
   extern __shared__ __align__(16) unsigned char smem[];
@@ -975,7 +979,7 @@ static int launch_fwd(const FwdParams& p0, cudaStream_t stream, int* grid_out, i
   p.jpat = tv == 32 ? 1u : 0xffffffffu / ((1u << tv) - 1u);
   p.vchunk = p.V < kMaxViewChunk ? p.V : kMaxViewChunk;
   p.num_tiles = (p.N + tv - 1) / tv;
-  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)4 * p.vchunk * 32 * 4, 16);
+  p.per_warp_bytes = (int)align_up(align_up((size_t)tv * (p.C + 1) * 4, 16) + (size_t)(tv == 32 ? 3 : 4) * p.vchunk * 32 * 4, 16);   // recorded depths only for partial tiles (push_records)
   const size_t smem = (size_t)p.per_warp_bytes * kFwdWarps;
   D3M_REQUIRE(smem <= 200 * 1024, D3M_ERR_ARG, "back_project: C=%d needs %zu B shared memory per CTA", p.C, smem);
   D3M_CUDA_CHECK(ensure_dynamic_smem(reinterpret_cast<const void*>(k), smem));

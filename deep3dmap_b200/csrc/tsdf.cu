@@ -4,12 +4,15 @@
 //
 // Design: the reference launches one thread per voxel of the WHOLE volume for every frame (134 M threads at
 // 512^3, >99 % of which exit at the frustum test) and copies seven arrays both ways per call.  Here
-//   * a tiny prep kernel reduces each frame's max depth (16 partial maxima per frame),
-//   * ONE persistent kernel handles any number of frames: every CTA derives the union of the frames' frustum
-//     boxes, walks the 8x8x16-voxel tiles inside it, culls frames per tile against the frustum planes,
-//     keeps the tile's tsdf/weight values in REGISTERS while it applies the surviving frames in order (the
-//     running average is order dependent), and writes back only what changed.  Volume bytes move once per
-//     launch instead of once per frame; z-fastest rows give coalesced 64-byte segments.
+// three launches handle up to 512 frames (two for up to 32):
+//   * tsdf_prep     reads every depth byte once, at HBM speed: max depth per 32x32-pixel block and per strip of blocks
+//                   (the coarse depth grid the culls test against);
+//   * tsdf_cull     for every 8x8x16-voxel tile inside the union of the frames' frustum boxes: one bit per frame that can
+//                   touch it (frustum planes + coarse depth, conservative), tiles listed by their first frame word;
+//   * tsdf_integrate  persistent, barrier-free: warps pull 4x4x8-voxel sub-boxes from one queue, keep the sub-box's
+//                   tsdf / weight in REGISTERS while they apply the surviving frames in order (the running average is
+//                   order dependent), and write back only what changed.  Volume bytes move once per launch instead of
+//                   once per frame; a lane row is 8 consecutive z = whole 32-byte sectors.
 // Per-voxel arithmetic is the reference's, rounding step for rounding step (explicit _rn intrinsics
 // reproducing the FMA contraction nvcc applies to the reference source; checked bit-for-bit against that
 // source compiled verbatim, see oracle/build_ref.py and tests/test_gpu_tsdf.py).
@@ -456,7 +459,7 @@ __global__ void __launch_bounds__(kCullThreads) tsdf_cull_kernel(const TsdfParam
 // got it down to 0.49 GB but lost the gain to waiting (a word touches only a sector of the scene, < 1.5 waves of items,
 // so the predecessor of an item is usually still running).
 // The only __syncthreads of the kernel is the one after staging the frames' hot data in shared memory: with CTA-wide
-// frame lists 37 % of the issue slots were lost at barriers (profiles/r02e_tsdf_ncu.txt).
+// frame lists a third of the warp stalls were barrier waits (profiles/r02e_tsdf_ncu.txt).
 template <int SEM, bool COLOR, bool SL>
 __global__ void __launch_bounds__(kTsdfThreads, 4) tsdf_integrate_kernel(const TsdfParams p) {
   extern __shared__ __align__(16) float s_hot[];   // (F, kHotFloats)
@@ -668,7 +671,7 @@ __global__ void __launch_bounds__(kTsdfThreads, 4) tsdf_integrate_kernel(const T
 // ------------------------------------------------------------------------------------------------
 // Host-side staging copy.  TSDFVolume.integrate() receives a pageable numpy frame (1.2 MB at 480x640); measured on the
 // B200 box a single-threaded memcpy into the pinned ring takes ~130 us and is 90 % of the per-frame cost of the
-// reference-shaped API (profiles/r01c_tsdf_host_profile.txt).  A few persistent helper threads split the copy.
+// reference-shaped API (profiles/r01f_tsdf_host_profile.txt).  A few persistent helper threads split the copy.
 // ------------------------------------------------------------------------------------------------
 class CopyPool {
  public:

@@ -12,6 +12,10 @@ the box, gloo in the CPU tests) for the few exchange steps the path really has (
       (3) `all_gather_rows` of the per-shard count / occupancy (or full rows) only where the next coarse-to-fine
           level needs the complete set (`neucon_network.py:132, 180-196`).
     Collectives are issued in a fixed order, so results are deterministic run to run.
+    `back_project_voxel_sharded_view_owner` is the same path with all three exchanges fused into the kernels over CUDA-IPC
+    peer memory (one NVSwitch box): the forward gather stores the view counts into every rank's full-scene buffer, the
+    backward gather stores each texel into the staging slot of the rank that owns the texel's view (reduce-scatter by view,
+    slots summed in rank order), and a mailbox kernel carries the 3 fp64 sums + barriers -- no NCCL call in the step.
   * TSDF x-slab sharding -- `tsdf_slab` gives each rank a contiguous range of x planes; integration needs no
     exchange at all; `TSDFVolume(..., slab=(x_begin, x_end))` + `gather_tsdf_volume` reassemble the volume.
 

@@ -2,7 +2,11 @@
 import json
 import sys
 
-p = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+_text = open(sys.argv[1]).read().strip()
+try:
+    p = json.loads(_text)                       # pretty-printed copy under profiles/
+except ValueError:
+    p = json.loads(_text.splitlines()[-1])      # raw bench output: the JSON line is the last one
 print("value %.3f G samples/s   ms/step graph %.4f eager %.4f host-issue %.4f   e2e %.3f ms   roofline.frac %.3f" % (
     p["value"] / 1e9, p["ms_per_step"], p["ms_per_step_eager"], p["host_issue_ms_per_step"], p["e2e"]["ms_per_step"],
     p["roofline"]["frac"]))
