@@ -65,6 +65,63 @@ def test_dense_levels_full_size(level):
     assert int(cnt.sum()) == S
 
 
+def _reference_on_this_gpu(inp):
+    """The unmodified reference back_project.py (oracle/_ref, staged by oracle/build_ref.py) run with its aten CUDA kernels."""
+    from oracle import ref_gpu
+    dev = torch.device("cuda:0")
+    ref_bp = ref_gpu.back_project_fn()
+    feats = torch.from_numpy(inp["feats"]).to(dev).requires_grad_(True)
+    vol, cnt = ref_bp(torch.from_numpy(inp["coords"]).to(dev), torch.from_numpy(inp["origin"]).to(dev), inp["voxel_size"], feats,
+                      torch.from_numpy(inp["KRcam"]).to(dev))
+    vol.backward(torch.from_numpy(inp["grad_out"]).to(dev))
+    torch.cuda.synchronize()
+    return vol.detach().cpu().numpy(), cnt.cpu().numpy(), feats.grad.cpu().numpy()
+
+
+def _check_vs_reference_gpu(name, inp):
+    C = inp["feats"].shape[2]
+    vol, cnt, g = run_cuda(inp)
+    r_vol, r_cnt, r_g = _reference_on_this_gpu(inp)
+    np.testing.assert_array_equal(cnt, r_cnt, err_msg=name + ": count vs the reference on this GPU")
+    np.testing.assert_array_equal(cnt > 1, r_cnt > 1)
+    # cuBLAS' bmm on the GPU and the CPU bmm the fixtures were recorded with round K.p differently in the last place; one ulp
+    # of a pixel coordinate of ~100 is 8e-6 of a pixel, i.e. of a bilinear weight: the reference's own two platforms differ
+    # by 1e-6 .. 1e-5 of the tensor's scale on single elements (measured here: relative L2 1.2e-6 / 3.5e-6 at levels 0 / 1,
+    # max 5e-6 / 1.2e-5).  Ours follows the CPU rounding sequence (bit-identical to the oracle, check_vs_oracle), so against the
+    # GPU run the bars are norm-wise and sized for that platform noise; a wrong texel or weight would miss them by orders
+    # of magnitude, and the counts -- integers -- must still agree exactly.
+    assert_close_norm(vol[:, :C], r_vol[:, :C], name + ": features vs the reference on this GPU", rel_l2=2e-5, rel_max=1e-4)
+    assert_close_norm(vol[:, C], r_vol[:, C], name + ": depth channel vs the reference on this GPU", rel_l2=2e-5, rel_max=1e-4)
+    assert_close_norm(g, r_g, name + ": grad_feats vs the reference on this GPU (its backward is atomicAdd-ordered)",
+                      rel_l2=2e-5, rel_max=1e-4)
+    return int(cnt.sum())
+
+
+def _have_staged_reference():
+    from oracle import ref_gpu
+    return ref_gpu.have_back_project()
+
+
+@pytest.mark.skipif(not _have_staged_reference(), reason="oracle/_ref/back_project.py not staged (reference tree absent)")
+def test_headline_fragment_vs_reference_on_this_gpu():
+    """The three calls of the bench's headline step (BASELINE config 2: level 0 dense fp32 coords, levels 1-2 sparse int64
+    coords) at full size against the UNMODIFIED reference file executed on the same GPU: counts and count>1 masks
+    bit-exact; features, depth channel and gradients norm-wise at the noise level between the reference's CPU and GPU
+    platforms (see _check_vs_reference_gpu; the element-wise 1e-5 bar is held against the CPU-pinned oracle elsewhere)."""
+    import bench
+    levels = bench.build_fragment_levels(lambda inp: run_cuda(inp, grad=False)[1])
+    assert [l["coords"].shape[0] for l in levels] == [13824, 27192, 109216]
+    for lv, inp in enumerate(levels):
+        _check_vs_reference_gpu("fragment level %d" % lv, inp)
+
+
+@pytest.mark.skipif(not _have_staged_reference(), reason="oracle/_ref/back_project.py not staged (reference tree absent)")
+def test_dense_level2_full_size_vs_reference_on_this_gpu():
+    """BASELINE config 1, finest level: 96^3 = 884,736 voxels x 9 views, C = 24 -- ours against the reference's aten path."""
+    S = _check_vs_reference_gpu("dense L2", cases.bp_level(2))
+    assert S == 3535706      # SURVEY.md section 8d, measured with the reference
+
+
 def test_backward_is_deterministic_bitwise():
     inp = cases.bp_level(1, 30000, np.int64)
     _, _, g1 = run_cuda(inp)
