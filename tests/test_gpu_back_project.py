@@ -250,6 +250,49 @@ def test_batched_fragments_equal_individual_calls():
         assert torch.equal(vol[mm], vb) and torch.equal(cnt[mm], cntb)
 
 
+def test_config4_64_fragments_one_call_equals_64_calls():
+    """BASELINE config 4 at FULL size (64 fragments x 9 views, the three levels of the headline fragment, B = 64 in one call
+    per level, exactly what bench.py's batched leg times): volume, count AND grad_feats of the batched call are bit-identical
+    to 64 single-fragment calls -- the fragment-parallel contract (back_project.py:28 loops the fragments; per-fragment depth
+    statistics, per-(view, fragment) gradient maps)."""
+    import bench
+    from deep3dmap_b200 import back_project
+    dev = torch.device("cuda:0")
+    levels = bench.build_fragment_levels(lambda inp: run_cuda(inp, grad=False)[1])
+    B = 64
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(77)
+    for lv, inp in enumerate(levels):
+        V, _, C, H, W = inp["feats"].shape
+        n1 = inp["coords"].shape[0]
+        c1 = torch.from_numpy(inp["coords"]).to(dev)
+        coords = c1.repeat(B, 1)
+        coords[:, 0] = torch.arange(B, device=dev).repeat_interleave(n1).to(coords.dtype)
+        origin = np.zeros((B, 3), np.float32)
+        KR = np.zeros((V, B, 4, 4), np.float32)
+        K = synth.scaled_K(synth.LEVELS[lv]["scale"])
+        for f in range(B):
+            off = (3.84 * (f % 8), 3.84 * (f // 8), 0.0)
+            origin[f] = off
+            R, c = synth.fragment_cameras(V, offset=off)
+            KR[:, f] = synth.krcam_from(R, c, K)
+        origin_d, KR_d = torch.from_numpy(origin).to(dev), torch.from_numpy(KR).to(dev)
+        feats = torch.randn((V, B, C, H, W), device=dev, generator=gen).requires_grad_(True)
+        go = torch.randn((n1 * B, C + 1), device=dev, generator=gen)
+        vol, cnt = back_project(coords, origin_d, inp["voxel_size"], feats, KR_d)
+        vol.backward(go)
+        assert int((cnt > 1).sum()) > n1 * B // 4
+        for f in range(0, B, 7 if lv == 2 else 1):          # every fragment at levels 0/1, every 7th at the finest level
+            fb = feats.detach()[:, f:f + 1].clone().requires_grad_(True)
+            vb, cb = back_project(c1, origin_d[f:f + 1], inp["voxel_size"], fb, KR_d[:, f:f + 1].contiguous())
+            vb.backward(go[f * n1:(f + 1) * n1])
+            sl = slice(f * n1, (f + 1) * n1)
+            assert torch.equal(cnt[sl], cb), "level %d fragment %d: count" % (lv, f)
+            assert torch.equal(vol[sl], vb), "level %d fragment %d: volume" % (lv, f)
+            assert torch.equal(feats.grad[:, f:f + 1], fb.grad), "level %d fragment %d: grad_feats" % (lv, f)
+        del feats, go, vol, cnt
+
+
 def test_backward_without_forward_count_recomputes_it():
     """C ABI contract: `count` is optional in d3m_back_project_bwd; both paths give identical bits, in both layouts."""
     from deep3dmap_b200 import voxel
