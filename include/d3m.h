@@ -144,7 +144,7 @@ int d3m_back_project_fwd_partial_x(const void* coords, int coords_kind, int64_t 
  *   cell_hist        binning state produced by d3m_back_project_fwd for the same inputs (its claim counters are used
  *                    and handed back cleared, so backward may run more than once), or NULL (then the state is rebuilt
  *                    in the workspace: clear + projection/histogram pass + scan, three extra launches)
- * Launches per call with count and cell_hist: fill+pre-division, gather -- two.
+ * Launches per call with count and cell_hist: fill + pre-division, order (rank sort of every bin), gather -- three.
  *   grad_feats       float32, fully overwritten; (V,B,H,W,C) when grad_nchw == 0, the reference's
  *                    (V,B,C,H,W) when grad_nchw != 0 (the gather kernel then stores channel-strided)
  * ------------------------------------------------------------------------------------------- */
