@@ -26,7 +26,8 @@ def step_serial():
         d["feats"].grad = None
         vol, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
         vol.backward(d["go"])
-streams = [torch.cuda.Stream() for _ in dl]
+# STEP_PRIO=1: the finest level's stream (the critical path of the three-branch graph) gets high priority
+streams = [torch.cuda.Stream(priority=(-1 if (os.environ.get("STEP_PRIO") == "1" and i == len(dl) - 1) else 0)) for i in range(len(dl))]
 def step_streams():      # STEP_STREAMS=1: one stream per level, largest level first (bench.py step_level_streams)
     cur = torch.cuda.current_stream()
     for d, st in sorted(zip(dl, streams), key=lambda x: -x[0]["coords"].shape[0]):
