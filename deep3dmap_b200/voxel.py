@@ -170,6 +170,8 @@ def _feats_layout(feats):
     (V,B,H,W,C) buffer) is used in place, anything else is handed over as contiguous NCHW and re-laid out by the library."""
     if feats.dim() != 5:
         raise ValueError("feats must be (n_views, batch, C, H, W)")
+    if feats.is_contiguous() and feats.shape[2] > 1 and feats.shape[3] * feats.shape[4] > 1:
+        return feats, _lib.FEATS_NCHW           # the reference's layout, the common case: no view object to build
     nhwc_view = feats.permute(0, 1, 3, 4, 2)
     if nhwc_view.is_contiguous():
         return nhwc_view, _lib.FEATS_NHWC
