@@ -396,3 +396,71 @@ def test_large_scene_config5_real_shape():
     vol, cnt, g = run_cuda(inp)
     assert int(cnt.astype(np.float64).sum()) == 36794117   # valid samples of the scene (oracle, build container)
     check_vs_oracle("large scene", inp, vol, cnt, g, grad_check=assert_close_norm)
+
+
+def test_cuda_graph_replay_is_bit_identical_to_eager():
+    """The headline number of bench.py is a CUDA-graph replay of forward + backward -- one branch, and one branch per level
+    on concurrent streams.  Replays must reproduce the eager results bit for bit, every time: the binning state is
+    self-cleaning (no clear launches between replays), scratch comes from the graph's pool (voxel._transient is bypassed
+    under capture) and programmatic dependent launch is off under capture."""
+    from deep3dmap_b200 import back_project
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    lv = []
+    for level, n_keep, dt in ((0, None, np.float32), (1, 30000, np.int64), (2, 60000, np.int64)):
+        inp = cases.bp_level(level, n_keep, dt)
+        lv.append(dict(coords=t(inp["coords"]), origin=t(inp["origin"]), vs=inp["voxel_size"],
+                       feats=t(inp["feats"]).requires_grad_(True), KR=t(inp["KRcam"]), go=t(inp["grad_out"])))
+
+    def one(d):
+        d["feats"].grad = None
+        vol, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+        vol.backward(d["go"])
+        return vol, cnt
+
+    eager = []
+    for d in lv:
+        vol, cnt = one(d)
+        eager.append((vol.detach().clone(), cnt.clone(), d["feats"].grad.clone()))
+        del vol, cnt      # no live autograd graph (and AccumulateGrad node bound to the default stream) going into the capture
+    streams = [torch.cuda.Stream() for _ in lv]
+
+    def serial():
+        return [one(d) for d in lv]
+
+    def branches():
+        cur = torch.cuda.current_stream()
+        outs = [None] * len(lv)
+        for i in reversed(range(len(lv))):
+            streams[i].wait_stream(cur)
+            with torch.cuda.stream(streams[i]):
+                outs[i] = one(lv[i])
+        for st in streams:
+            cur.wait_stream(st)
+        return outs
+
+    for name, fn in (("one branch", serial), ("branch per level", branches)):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            del_me = fn()
+        del del_me
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            outs = fn()
+        for rep in range(3):
+            for (vol, cnt), d in zip(outs, lv):          # poison the captured outputs: a replay must rewrite all of them
+                vol.detach().fill_(float("nan")); cnt.fill_(-1.0); d["feats"].grad.fill_(float("nan"))
+            g.replay()
+            torch.cuda.synchronize()
+            for i, ((vol, cnt), d) in enumerate(zip(outs, lv)):
+                assert torch.equal(cnt, eager[i][1]), "%s, replay %d, level %d: count" % (name, rep, i)
+                assert torch.equal(vol.detach(), eager[i][0]), "%s, replay %d, level %d: volume" % (name, rep, i)
+                assert torch.equal(d["feats"].grad, eager[i][2]), "%s, replay %d, level %d: grad_feats" % (name, rep, i)
+        del g, outs
+    # and eager still works (and agrees) after the graphs are gone
+    for i, d in enumerate(lv):
+        vol, cnt = one(d)
+        assert torch.equal(vol.detach(), eager[i][0]) and torch.equal(d["feats"].grad, eager[i][2])
