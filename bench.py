@@ -449,14 +449,15 @@ def run_ours(args, rank, world, local_rank):
 
     def step_level_streams():
         cur = torch.cuda.current_stream()
-        outs = []
-        for d, st in sorted(zip(dl, lvl_streams), key=lambda x: -x[0]["coords"].shape[0]):
+        outs = [None] * len(dl)
+        for i in sorted(range(len(dl)), key=lambda i: -dl[i]["coords"].shape[0]):
+            d, st = dl[i], lvl_streams[i]
             st.wait_stream(cur)
             with torch.cuda.stream(st):
                 d["feats"].grad = None
                 vol, cnt = back_project(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
                 vol.backward(d["go"])
-                outs.append((vol, cnt))
+                outs[i] = (vol, cnt)
         for st in lvl_streams:
             cur.wait_stream(st)
         return outs
@@ -531,7 +532,15 @@ def run_ours(args, rank, world, local_rank):
     for _ in range(3):
         step_one_backward()
     ms_eager_1b = timed(step_one_backward)
-    def capture(fn):
+    # eager results of the same step: every replayed graph must reproduce them bit for bit (asserted below -- the timed
+    # replay does all the work of the eager step, nothing is cached or skipped)
+    eager_ref = []
+    for (vol, cnt), d in zip(step_resident(), dl):
+        eager_ref.append((vol.detach().clone(), cnt.clone(), d["feats"].grad.clone()))
+    del vol, cnt
+    graph_checks = {}
+
+    def capture(fn, name):
         try:
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
@@ -541,24 +550,29 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                fn()
+                outs = fn()
             for _ in range(3):
                 g.replay()
             torch.cuda.synchronize()
-            return g, None
         except Exception as err:  # capture is an optimisation, never a requirement
             torch.cuda.synchronize()
             return None, repr(err)[:200]
+        same = all(torch.equal(vol.detach(), ref[0]) and torch.equal(cnt, ref[1]) and torch.equal(d["feats"].grad, ref[2])
+                   for (vol, cnt), d, ref in zip(outs, dl, eager_ref))
+        graph_checks[name] = bool(same)
+        if not same:
+            raise AssertionError("CUDA-graph replay (%s) does not reproduce the eager step bit for bit" % name)
+        return g, None
 
     graph, graph_err, graph_lv, graph_lv_err = None, None, None, None
     ms_eager_lv = None
     if not args.no_graph:
-        graph, graph_err = capture(step_resident)
+        graph, graph_err = capture(step_resident, "one_branch")
         if os.environ.get("D3M_BENCH_LEVEL_STREAMS", "1") != "0":
             for _ in range(3):
                 step_level_streams()
             ms_eager_lv = timed(step_level_streams)
-            graph_lv, graph_lv_err = capture(step_level_streams)
+            graph_lv, graph_lv_err = capture(step_level_streams, "branch_per_level")
     ms_graph_serial = timed(graph.replay) if graph is not None else None
     ms_graph_lv = timed(graph_lv.replay) if graph_lv is not None else None
     ms_graph = ms_graph_serial
@@ -790,6 +804,7 @@ def run_ours(args, rank, world, local_rank):
                             "small eager calls, plain stream order under graph capture and for large launches (D3M_PDL=auto)"),
         "ms_per_step_graph": ms_graph, "ms_per_step_graph_serial": ms_graph_serial,
         "ms_per_step_graph_level_streams": ms_graph_lv, "graph_error": graph_err or graph_lv_err,
+        "graph_replay_equals_eager_bitwise": graph_checks,
         "roofline": {"bound": "hbm", "kernel": "whole step: back_project fwd+bwd x 3 levels (every kernel of the path)",
                      "achieved": path_gbs, "peak": peak_gbs, "unit": "GB/s", "frac": path_gbs / peak_gbs,
                      "frac_of_nominal_8TBs": path_gbs / 8000.0, "peak_source": peak_src,
