@@ -309,6 +309,27 @@ def bench_reference_gpu(torch, dev, levels, flush_buf, steps, our_ms_step, our_d
     ms, ms_min = timed(lambda: reference_step(tl, bp), max(5, steps))
     res["fragment"] = {"ms_per_step": ms, "ms_per_step_best": ms_min, "samples_per_s": samples / (ms * 1e-3),
                        "ours_ms_per_step": our_ms_step, "speedup_ours": ms / our_ms_step if our_ms_step else None}
+    # same inputs, both implementations, on this GPU: counts must agree exactly; features / gradients are compared
+    # norm-wise (the reference's cuBLAS bmm rounds the projection differently from its CPU path, which ours is pinned to)
+    from deep3dmap_b200 import back_project as ours_bp
+    par = []
+    for lv, d in enumerate(tl):
+        d["feats"].grad = None
+        r_vol, r_cnt = bp(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+        r_vol.backward(d["go"])
+        r_grad = d["feats"].grad
+        f2 = d["feats"].detach().clone().requires_grad_(True)
+        o_vol, o_cnt = ours_bp(d["coords"], d["origin"], d["vs"], f2, d["KR"])
+        o_vol.backward(d["go"])
+        rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+        par.append({"level": lv, "count_bit_equal": bool(torch.equal(o_cnt, r_cnt)),
+                    "volume_rel_l2": rel(o_vol.detach(), r_vol.detach()), "grad_rel_l2": rel(f2.grad, r_grad)})
+        del r_vol, r_cnt, o_vol, o_cnt, f2
+    ok = all(q["count_bit_equal"] and q["volume_rel_l2"] <= 5e-5 and q["grad_rel_l2"] <= 5e-5 for q in par)
+    res["fragment"]["parity_vs_reference_on_this_gpu"] = {"levels": par, "bars": {"count": "bit-equal", "rel_l2": 5e-5},
+                                                          "pass": bool(ok)}
+    if not ok:
+        raise AssertionError("bench: ours disagrees with the reference on this GPU: %r" % (par,))
     del tl
     inp = synth.fragment_level_inputs(2)
     inp["grad_out"] = synth.grad_out_for(inp["coords"].shape[0], synth.LEVELS[2]["C"])
@@ -690,6 +711,8 @@ def run_ours(args, rank, world, local_rank):
             ref_gpu_res = {"back_project": bench_reference_gpu(torch, dev, levels, flush_buf, args.steps, ms_step,
                                                                dense["ms_fwd_bwd"] if dense else None),
                            "tsdf": bench_reference_gpu_tsdf(torch, dev)}
+        except AssertionError:    # ... except a parity failure against the reference: that must be loud
+            raise
         except Exception as err:  # a baseline leg never takes the headline line down
             log("reference_gpu leg failed:", repr(err))
             ref_gpu_res = {"error": repr(err)[:300]}
