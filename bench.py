@@ -215,10 +215,11 @@ def reference_step(tl, bp):
         vol.backward(d["go"])
 
 
-def cpu_reference_bp(levels, steps, warmup):
+def cpu_reference_bp(levels, steps, warmup, keep_outputs=False):
     """The reference's own CPU path: oracle/_ref/back_project.py (byte-for-byte copy of the reference file) executed by
     torch on all host cores; `.cuda()` is shimmed to the identity for the duration of the calls.  -> (samples/s, s/step,
-    threads) or None when the staged file is absent."""
+    threads[, outputs]) or None when the staged file is absent; `outputs` = per level (volume, count, grad_feats) of one
+    more, untimed step (for the in-run parity check of our arm)."""
     from oracle import ref_gpu
     if not ref_gpu.have_back_project():
         return None
@@ -237,6 +238,15 @@ def cpu_reference_bp(levels, steps, warmup):
             ts.append(time.perf_counter() - t0)
     samples = sum(l["coords"].shape[0] for l in levels) * synth.N_VIEWS
     sec = sum(ts) / len(ts)
+    if keep_outputs:
+        outs = []
+        with ref_gpu.cpu_shim():
+            for d in tl:
+                d["feats"].grad = None
+                vol, cnt = bp(d["coords"], d["origin"], d["vs"], d["feats"], d["KR"])
+                vol.backward(d["go"])
+                outs.append((vol.detach(), cnt.detach(), d["feats"].grad))
+        return samples / sec, sec, torch.get_num_threads(), outs
     return samples / sec, sec, torch.get_num_threads()
 
 
@@ -795,9 +805,28 @@ def run_ours(args, rank, world, local_rank):
     cpu_base = None
     if world == 1:  # reported on rank 0 at N=1 only (the ranks of a multi-GPU run share the host cores)
         port_v, port_sec, port_cores = cpu_baseline_bp(levels, 5, 1)
-        ref = None if args.no_reference_cpu else cpu_reference_bp(levels, 5, 1)
+        ref = None if args.no_reference_cpu else cpu_reference_bp(levels, 5, 1, keep_outputs=True)
         if ref is not None:
+            # our arm against the reference's CPU run of the same inputs, in this very process (the pin of the parity
+            # contract: the fixtures under tests/golden were recorded from this path)
+            par = []
+            for lv, ((o_vol, o_cnt, o_grad), (r_vol, r_cnt, r_grad)) in enumerate(zip(eager_ref, ref[3])):
+                C = r_vol.shape[1] - 1
+                ov, og = o_vol.cpu(), o_grad.cpu()
+                rel = lambda a, b: float((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30))
+                par.append({"level": lv, "count_bit_equal": bool(torch.equal(o_cnt.cpu(), r_cnt)),
+                            "feature_elements_not_bit_equal": int((ov[:, :C] != r_vol[:, :C]).sum()),
+                            "feature_elements": int(r_vol[:, :C].numel()),
+                            "features_rel_l2": rel(ov[:, :C], r_vol[:, :C]), "depth_channel_rel_l2": rel(ov[:, C], r_vol[:, C]),
+                            "grad_rel_l2": rel(og, r_grad)})
+            ok = all(q["count_bit_equal"] and q["features_rel_l2"] <= 1e-6 and q["depth_channel_rel_l2"] <= 1e-5
+                     and q["grad_rel_l2"] <= 1e-6 for q in par)
+            if not ok:
+                raise AssertionError("bench: ours disagrees with the reference's CPU run of the same inputs: %r" % (par,))
             cpu_base = {"value": ref[0], "unit": "samples/s", "cores": ref[2], "kind": "reference",
+                        "parity_ours_vs_this_run": {"levels": par, "pass": True,
+                                                    "bars": {"count": "bit-equal", "features_rel_l2": 1e-6,
+                                                             "depth_channel_rel_l2": 1e-5, "grad_rel_l2": 1e-6}},
                         "sample": "5 full steps of the same fragment through the unmodified reference back_project.py on "
                                   "the host (torch CPU ops + autograd; %.0f ms/step)" % (ref[1] * 1e3),
                         "port": {"value": port_v, "unit": "samples/s", "cores": port_cores, "ms_per_step": port_sec * 1e3,
