@@ -568,11 +568,16 @@ static gather_kernel_t pick_gather_kernel(int C) {
 // Measured on B200 (profiles/r01_bp_gather_tile.txt): small tiles win -- more CTAs per SM hide the dependent
 // bin_start -> entry -> row load chain better than a smaller halo helps -- down to 8x4 texels; C = 24 -> 8x8 (31 KB),
 // C = 40 -> 8x4 (29 KB), C = 80 -> 8x4 (58 KB).
-static void pick_gather_tile(int C, int& TX, int& TY, size_t& smem) {
+// Exception, measured in round 2 (profiles/r02z_gather_tile_density.txt): at C = 24 and FEW voxels per pixel (sparse
+// fragment levels: ~6 voxels per pixel, ~4 entries per bilinear cell) the walk over cells, not the rows, is the cost, and
+// the 16x8 tile (59 KB, 1.13 cells per texel instead of 1.27) is faster -- level-2 gather 49.9 -> 46.2 us, 64 fragments
+// 10.9 -> 10.6 ms -- while dense volumes (46 voxels per pixel and more) stay on 8x8 (dense gather 115 vs 120 us).
+static void pick_gather_tile(int C, double voxels_per_pixel, int& TX, int& TY, size_t& smem) {
   static const int ladder[][2] = {{16, 8}, {8, 8}, {8, 4}, {4, 4}, {2, 2}, {1, 1}};
   static const int env_kb = getenv("D3M_GATHER_SMEM_KB") ? atoi(getenv("D3M_GATHER_SMEM_KB")) : 0;  // tuning aid
+  const bool sparse_small_c = C <= 24 && voxels_per_pixel < 16.0;
   for (int pass = 0; pass < 2; ++pass) {
-    const size_t budget = env_kb ? (size_t)env_kb * 1024 : (pass == 0 ? 32 * 1024 : 64 * 1024);
+    const size_t budget = env_kb ? (size_t)env_kb * 1024 : ((pass == 0 && !sparse_small_c) ? 32 * 1024 : 64 * 1024);
     for (auto& t : ladder) {
       TX = t[0]; TY = t[1];
       smem = (size_t)16 * C * (TX + 1) * (TY + 1);
@@ -632,7 +637,7 @@ static int launch_bwd(BwdParams p, const BinState& bins, const BinLayout& bl, bo
   if (k) {
     int TX, TY;
     size_t smem;
-    pick_gather_tile(p.C, TX, TY, smem);
+    pick_gather_tile(p.C, (double)p.N / ((double)p.B * p.H * p.W), TX, TY, smem);
     const int tiles_x = (p.W + TX - 1) / TX, tiles_y = (p.H + TY - 1) / TY;
     const int64_t tiles = (int64_t)p.V * p.B * tiles_x * tiles_y;
     D3M_REQUIRE(tiles < (1ll << 31), D3M_ERR_ARG, "back_project backward: too many gather tiles");
