@@ -176,3 +176,22 @@ def test_partitions_cover_everything():
         x = torch.arange(n) * 3 + 1
         inv = shard.blocks_inverse_permutation(n, w, block=blk)
         assert torch.equal(torch.cat([x[p] for p in parts])[inv], x)
+
+
+def test_count_exchange_row_map_matches_the_partitions():
+    """`d3m_count_exchange` (include/d3m.h): the forward gather kernel stores voxel n's count at global row
+    begin + n (contiguous range) or ((n / block) * world + rank) * block + n % block (block-cyclic).  That arithmetic
+    must name exactly the rows `voxel_range` / `voxel_blocks` hand to the rank -- including ragged tails and ranks
+    that own no block."""
+    from deep3dmap_b200 import shard
+    for N, world, block in ((10, 3, 4), (4096 * 5 + 17, 4, 4096), (100, 8, 16), (7, 8, 4), (64, 2, 8)):
+        seen = torch.zeros(N, dtype=torch.int32)
+        for rank in range(world):
+            idx = shard.voxel_blocks(N, rank, world, block=block)
+            n = torch.arange(idx.numel(), dtype=torch.int64)
+            rows = ((n // block) * world + rank) * block + n % block
+            assert torch.equal(rows, idx), (N, world, block, rank)
+            seen[idx] += 1
+            b, e = shard.voxel_range(N, rank, world)
+            assert torch.equal(b + torch.arange(e - b), torch.arange(b, e))
+        assert bool((seen == 1).all())
